@@ -1,0 +1,211 @@
+/*
+ * uvt.h — C ABI of the B200-native voxel ray-traversal pass.
+ *
+ * This is the drop-in boundary for the reference engine's renderer entry points
+ * (SURVEY.md §8b).  Every export below names the reference interface it replaces
+ * (paths relative to the reference checkout).  Plain pointers and sizes only; no
+ * torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative uvt_status; the message is
+ *     available through uvt_last_error().  Nothing aborts (the reference @panic's).
+ *   - one ctx per host thread; all device work of a ctx is issued on ONE CUDA stream
+ *     in call order (the reference uses one in-order GL queue + glMemoryBarrier,
+ *     src/engine/graphics/shader.zig:113-117).  Dispatches are asynchronous like
+ *     glDispatchCompute; uvt_sync()/uvt_readback() wait.
+ *   - there is no CPU fallback: without a CUDA device uvt_create() fails.
+ */
+#ifndef UVT_H
+#define UVT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UVT_ABI_VERSION 1
+
+typedef enum uvt_status {
+    UVT_OK = 0,
+    UVT_ERR_INVALID = -1,  /* bad argument / call order                      */
+    UVT_ERR_CUDA = -2,     /* CUDA runtime error (message has the detail)    */
+    UVT_ERR_NO_DEVICE = -3,/* no usable CUDA device: there is no CPU path    */
+    UVT_ERR_OOM = -4,
+    UVT_ERR_FORMAT = -5,   /* malformed .vox / world dump                    */
+    UVT_ERR_IO = -6
+} uvt_status;
+
+/* ---- parameters: every constant the reference hard-codes in source ------------- */
+typedef struct uvt_params {
+    uint32_t map_dim;            /* MAP_DIMENSION, blocks per axis  (assets/shaders/map.glsl:2; src/game.zig:33) */
+    uint32_t primary_max_steps;  /* 192  (assets/shaders/primary.comp.glsl:43)   */
+    uint32_t shadow_max_steps;   /* 48   (assets/shaders/secondary.comp.glsl:41) */
+    uint32_t edit_max_steps;     /* 64   (assets/shaders/terrain_edit.comp.glsl:16) */
+    float    epsilon;            /* EPSILON 0.001 (assets/shaders/map.glsl:7)    */
+    uint32_t flags;              /* UVT_FLAG_*                                    */
+    uint32_t layout;             /* uvt_layout: which device world layout the traversal kernels read */
+    uint32_t reserved[9];
+} uvt_params;
+
+enum {
+    UVT_FLAG_HIT_BUFFER = 1u << 0, /* also write the explicit hit buffer (uvt_hit) in the primary pass */
+    UVT_FLAG_ENTITIES   = 1u << 1  /* shadow pass runs traceEntities (map.glsl:172-201); on by default */
+};
+
+typedef enum uvt_layout {
+    UVT_LAYOUT_COMPACT   = 0, /* B200 layout: chunk-occupancy window + 8-bit material bricks + model bitmasks */
+    UVT_LAYOUT_REFERENCE = 1  /* the reference SSBO layout read verbatim (u32 chunk table + u32[512] bricks + RGBA8 atlas) */
+} uvt_layout;
+
+void uvt_default_params(uvt_params *p);
+
+/* ---- camera: src/engine/graphics/camera.zig:12-16 == camera.glsl:2-6 (std140) --- */
+typedef struct uvt_camera {
+    float cam_pos[4];   /* C_position (w unused)                        @0  */
+    float cam_mat[16];  /* C_view: 4 rows of F32x4 = 4 GLSL columns     @16 */
+    float fov;          /* radians                                      @80 */
+    float _pad[3];      /* std140 tail                                  @84 */
+} uvt_camera;           /* 96 bytes */
+
+/* ---- explicit hit buffer (new; the reference never materialises it) */
+typedef struct uvt_hit {
+    uint32_t px, py, pz; /* hit sub-voxel coordinate `pos` (map.glsl:108); 0xFFFFFFFF on miss */
+    uint32_t block;      /* block word: ty | is_solid<<28 (src/engine/voxel.zig:7-19); 0 on miss */
+    uint32_t color;      /* atlas texel R|G<<8|B<<16|A<<24 (= HitInfo.data); 0 on miss          */
+    float    distance;   /* length(hit_pos/8 - rayOrigin) in blocks, fp32; -1 on miss            */
+    uint16_t trips;      /* DDA loop trips executed (map.glsl:106)                               */
+    uint8_t  face;       /* faceId 1..6 (map.glsl:119-125), 0 = miss                             */
+    uint8_t  exit_kind;  /* 0 hit, 1 step cap exhausted, 2 left the map                          */
+} uvt_hit;               /* 28 bytes */
+
+/* Exact per-pass traversal counters; they define the ALGORITHMIC bytes of SURVEY §8d:
+ * bytes = 4*t_in + 4*t_chunk + 4*t_block + per-pixel G-buffer traffic. */
+typedef struct uvt_counters {
+    uint64_t rays;       /* rays traced (pixels that ran traceMap)                         */
+    uint64_t t_in;       /* loop trips that passed the bounds test (one chunks[] read)     */
+    uint64_t t_chunk;    /* trips whose chunk entry != 0 (one data[] read)                 */
+    uint64_t t_block;    /* trips whose block != 0 (one atlas read)                        */
+    uint64_t hits;       /* rays that returned a hit                                       */
+    uint64_t early_out;  /* secondary only: pixels that left at secondary.comp.glsl:26-29  */
+} uvt_counters;
+
+typedef struct uvt_ctx uvt_ctx;
+typedef struct uvt_pipeline uvt_pipeline;
+
+/* ---- context: gfx.init / enableDebug (src/engine/graphics/graphics.zig:43-75) ---- */
+int  uvt_create(const uvt_params *params, int device, uvt_ctx **out);
+void uvt_destroy(uvt_ctx *ctx);
+/* ctx may be NULL: returns the calling thread's last creation-time error. */
+const char *uvt_last_error(uvt_ctx *ctx);
+int  uvt_abi_version(void);
+/* Issue all further work on an externally owned cudaStream_t (NULL restores the ctx's own stream). */
+int  uvt_set_stream(uvt_ctx *ctx, void *cuda_stream);
+int  uvt_get_params(uvt_ctx *ctx, uvt_params *out);
+/* Switch the device world layout the traversal kernels read (both stay resident after a commit). */
+int  uvt_set_layout(uvt_ctx *ctx, uint32_t layout);
+/* The layout actually in use: COMPACT needs <= 255 distinct block words, else REFERENCE is used. */
+int  uvt_effective_layout(uvt_ctx *ctx);
+/* Step caps (reference constants 192 / 48: primary.comp.glsl:43, secondary.comp.glsl:41). */
+int  uvt_set_max_steps(uvt_ctx *ctx, uint32_t primary, uint32_t shadow);
+
+/* ---- pipelines: ComputePipeline / RasterPipeline init+deinit (shader.zig:97-153) --
+ * Kernels are precompiled, so a pipeline is an opaque token naming a pass; creating one
+ * checks that the kernel image for this device is loadable (the analogue of compile+link),
+ * and hot-reload (src/game.zig:258-288) is create-new + destroy-old. */
+typedef enum uvt_pipeline_kind {
+    UVT_PIPELINE_PRIMARY = 0,   /* assets/shaders/primary.comp.glsl   */
+    UVT_PIPELINE_SECONDARY = 1, /* assets/shaders/secondary.comp.glsl */
+    UVT_PIPELINE_EDIT = 2,      /* assets/shaders/terrain_edit.comp.glsl */
+    UVT_PIPELINE_BLIT = 3       /* assets/shaders/blit.{vertex,fragment}.glsl */
+} uvt_pipeline_kind;
+int  uvt_pipeline_create(uvt_ctx *ctx, uvt_pipeline_kind kind, uvt_pipeline **out);
+void uvt_pipeline_destroy(uvt_pipeline *p);
+/* ComputePipeline.dispatch(x,y,z) (shader.zig:113-117): group counts are accepted for
+ * signature parity and validated against the G-buffer ((W/32+1)x(H/32+1), game.zig:241-242),
+ * the pass always covers the whole G-buffer.  RasterPipeline.draw(4) maps to kind BLIT. */
+int  uvt_pipeline_dispatch(uvt_pipeline *p, uint32_t gx, uint32_t gy, uint32_t gz);
+
+/* ---- world: VoxelBrickmap + GpuBlockAllocator (src/engine/voxel.zig:25-82,
+ *      src/engine/graphics/gpu_block_allocator.zig:4-41, buffer.zig:80-134) ---------
+ * The reference host writes chunk table and brick pool in place through persistent
+ * mappings.  Here the ctx hands out PINNED host staging with the same layout
+ * (chunks: u32[(dim/8)^3], 0 = empty else brick+1; bricks: u32[capacity][512],
+ * index x%8 + 8*(y%8) + 64*(z%8)); uvt_world_commit() uploads and repacks it. */
+int  uvt_world_alloc(uvt_ctx *ctx, uint32_t dim, uint32_t **chunks_host, uint32_t **bricks_host, size_t brick_capacity);
+/* GpuBlockAllocator.alloc growth (gpu_block_allocator.zig:20-24 → buffer.zig:48-62): contents are preserved. */
+int  uvt_world_grow(uvt_ctx *ctx, size_t new_capacity, uint32_t **bricks_host);
+/* Make host edits visible to the GPU (H2D + repack kernel). n_bricks = GpuBlockAllocator.block_index. */
+int  uvt_world_commit(uvt_ctx *ctx, size_t n_bricks);
+
+/* ---- atlas: VoxelModelAtlas → Texture.set_data_offset → glTextureSubImage3D
+ *      (voxel.zig:88-131, texture.zig:70-72): RGBA8 sub-box, x fastest then y then z. */
+int  uvt_atlas_upload(uvt_ctx *ctx, uint32_t ox, uint32_t oy, uint32_t oz,
+                      uint32_t w, uint32_t h, uint32_t d, const uint32_t *rgba);
+
+/* ---- camera UBO: PersistentMappedBuffer(UniformData) (game.zig:94,224-229,235) ---- */
+int  uvt_set_camera(uvt_ctx *ctx, const uvt_camera *cam);
+/* Batched poses (BASELINE config 5): pose i renders into G-buffer layer i. */
+int  uvt_set_cameras(uvt_ctx *ctx, const uvt_camera *cams, int n);
+
+/* ---- G-buffer: GBuffer.init/resize (gbuffer.zig:9-30; game.zig:91,197-205) -------- */
+int  uvt_resize(uvt_ctx *ctx, uint32_t width, uint32_t height);
+/* Multi-GPU image partition: this ctx renders only the row bands b with
+ * b % n_parts == part (band = band_rows image rows) of the full WxH frame, stored
+ * compactly band after band.  n_parts = 1 restores whole-frame rendering. */
+int  uvt_set_partition(uvt_ctx *ctx, uint32_t band_rows, uint32_t n_parts, uint32_t part);
+/* rows this ctx renders under the current partition */
+int  uvt_local_rows(uvt_ctx *ctx, uint32_t *rows);
+
+/* ---- passes: game.zig:244-255 ------------------------------------------------------ */
+int  uvt_dispatch_primary(uvt_ctx *ctx);    /* primary.comp.glsl main   */
+int  uvt_dispatch_secondary(uvt_ctx *ctx);  /* secondary.comp.glsl main */
+int  uvt_shade(uvt_ctx *ctx);               /* blit.fragment.glsl main → RGBA8 frame */
+/* primary+secondary+shade in one launch; results identical to the three calls above */
+int  uvt_dispatch_frame(uvt_ctx *ctx);
+/* terrain_edit.comp.glsl: the centre pick ray, traceMap(...,64); returns the hit. */
+int  uvt_pick(uvt_ctx *ctx, uvt_hit *out);
+int  uvt_sync(uvt_ctx *ctx);
+
+typedef enum uvt_buffer_kind {
+    UVT_BUF_ALBEDO = 0,       /* RGBA8   4 B/px  (image unit 0) */
+    UVT_BUF_NORMAL = 1,       /* RGBA8   4 B/px  (image unit 1) */
+    UVT_BUF_POSITION = 2,     /* RGBA32F 16 B/px (image unit 2) */
+    UVT_BUF_ILLUMINATION = 3, /* RGBA8   4 B/px  (image unit 3) */
+    UVT_BUF_FRAME = 4,        /* RGBA8   4 B/px  default framebuffer after the blit */
+    UVT_BUF_HIT = 5           /* uvt_hit 28 B/px (needs UVT_FLAG_HIT_BUFFER) */
+} uvt_buffer_kind;
+/* Row 0 is the BOTTOM image row (GL image origin). Copies layer 0..n_layers-1 back to back. */
+int  uvt_readback(uvt_ctx *ctx, uvt_buffer_kind kind, void *dst, size_t bytes);
+size_t uvt_buffer_bytes(uvt_ctx *ctx, uvt_buffer_kind kind);
+/* Device address of a buffer (for NCCL / peer access by the caller's communication layer). */
+int  uvt_device_ptr(uvt_ctx *ctx, uvt_buffer_kind kind, void **dptr);
+/* Redirect the FRAME output to caller-owned device memory (may be a peer-mapped
+ * pointer of another GPU: finished bands are then stored straight over NVLink). */
+int  uvt_bind_frame_target(uvt_ctx *ctx, void *dptr, uint32_t reserved, uint32_t global_rows);
+/* Rank 0 after the NCCL gather: `gathered` holds n_parts compact band buffers of rows_per_part rows
+ * back to back; writes the assembled WxH frame (one kernel on the ctx stream). */
+int  uvt_deinterleave(uvt_ctx *ctx, const void *gathered, void *frame, uint32_t rows_per_part);
+/* Pinned host memory for readback targets / upload sources (the e2e path of bench.py). */
+int  uvt_alloc_pinned(uvt_ctx *ctx, size_t bytes, void **out);
+int  uvt_free_pinned(uvt_ctx *ctx, void *p);
+
+/* Exact traversal counters of the last primary (which=0) / secondary (which=1) pass run
+ * with counting on; uvt_count_pass re-runs that pass with the counting kernel variant. */
+int  uvt_count_pass(uvt_ctx *ctx, int which, uvt_counters *out);
+/* Device time of the last dispatch of each pass, measured with CUDA events on the ctx stream. */
+int  uvt_last_pass_ms(uvt_ctx *ctx, int which /*0 primary,1 secondary,2 shade,3 frame*/, float *ms);
+int  uvt_enable_timing(uvt_ctx *ctx, int on);
+/* Number of kernels this ctx has launched since creation. */
+uint64_t uvt_launch_count(uvt_ctx *ctx);
+
+/* Utility kernel for measuring the L2 read bandwidth roofline denominator:
+ * repeatedly reads an L2-resident buffer of `bytes` with 16-B loads; returns GB/s. */
+int  uvt_measure_l2_read_gbps(uvt_ctx *ctx, size_t bytes, int repeats, float *gbps);
+int  uvt_measure_hbm_copy_gbps(uvt_ctx *ctx, size_t bytes, int repeats, float *gbps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UVT_H */

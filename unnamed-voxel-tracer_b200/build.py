@@ -1,0 +1,70 @@
+"""Build the in-tree shared library (CUDA kernels + C ABI + host formats) for sm_100a.
+
+nvcc cross-compiles without a GPU.  The .so stays in-tree (git-ignored) so it travels to
+the GPU box with the snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libuvt.so")
+
+SOURCES = [
+    os.path.join(CSRC, "uvt.cu"),
+    os.path.join(CSRC, "host", "noise.cpp"),
+    os.path.join(CSRC, "host", "world.cpp"),
+    os.path.join(CSRC, "host", "vox.cpp"),
+    os.path.join(CSRC, "host", "atlas.cpp"),
+    os.path.join(CSRC, "host", "camera.cpp"),
+]
+HEADERS = [
+    os.path.join(CSRC, "trace.cuh"),
+    os.path.join(CSRC, "kernels.cuh"),
+    os.path.join(ROOT, "include", "uvt.h"),
+    os.path.join(ROOT, "include", "uvt_host.h"),
+]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",            # every fp32 op individually rounded: bit-exact parity with the oracle
+    "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fno-fast-math,-Wall",
+    "-shared", "-cudart", "static",
+    "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS + [os.path.abspath(__file__)])
+
+
+def build(force=False, verbose=False):
+    if not force and not is_stale():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("nvcc failed building libuvt.so")
+    if verbose:
+        print(r.stdout)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,245 @@
+// VoxelBrickmap + GpuBlockAllocator + procgen, host side.
+//
+// Mirrors src/engine/voxel.zig:25-82 (VoxelBrickmap), src/engine/graphics/
+// gpu_block_allocator.zig:4-41 (bump allocator with x2 growth) and src/procgen.zig:6-70.
+// When attached to a uvt_ctx the storage is the ctx's pinned staging (uvt_world_alloc /
+// uvt_world_grow), the analogue of the reference's persistently mapped GL buffers.
+#include "uvt_host.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <new>
+
+struct uvt_brickmap {
+    uvt_ctx *ctx = nullptr;
+    uint32_t dim = 0;       // blocks per axis
+    uint32_t cdim = 0;      // chunks per axis = dim / 8
+    uint32_t *chunks = nullptr;
+    uint32_t *bricks = nullptr;
+    size_t block_index = 0;      // next free brick
+    size_t max_block_index = 0;  // capacity in bricks
+};
+
+namespace {
+
+constexpr uint32_t kChunk = 8;
+constexpr size_t kBrickWords = 512;
+
+inline size_t pos_to_index(size_t dim, size_t x, size_t y, size_t z) { return x + dim * (y + z * dim); }
+
+// GpuBlockAllocator.alloc: gpu_block_allocator.zig:20-30
+int brick_alloc(uvt_brickmap *bm, size_t *out) {
+    if (bm->block_index >= bm->max_block_index) {
+        size_t new_cap = bm->max_block_index * 2;
+        if (bm->ctx) {
+            uint32_t *nb = nullptr;
+            int rc = uvt_world_grow(bm->ctx, new_cap, &nb);
+            if (rc != UVT_OK) return rc;
+            bm->bricks = nb;
+        } else {
+            uint32_t *nb = (uint32_t *)std::realloc(bm->bricks, new_cap * kBrickWords * sizeof(uint32_t));
+            if (!nb) return UVT_ERR_OOM;
+            // fresh blocks read as zero (the reference relies on GL zero-initialised storage)
+            std::memset(nb + bm->max_block_index * kBrickWords, 0,
+                        (new_cap - bm->max_block_index) * kBrickWords * sizeof(uint32_t));
+            bm->bricks = nb;
+        }
+        bm->max_block_index = new_cap;
+    }
+    *out = bm->block_index++;
+    return UVT_OK;
+}
+
+// VoxelBrickmap.get_block_for_chunk: voxel.zig:47-56
+int block_for_chunk(uvt_brickmap *bm, size_t chx, size_t chy, size_t chz, size_t *out) {
+    uint32_t &slot = bm->chunks[pos_to_index(bm->cdim, chx, chy, chz)];
+    if (slot > 0) {
+        *out = slot - 1;
+        return UVT_OK;
+    }
+    size_t idx;
+    int rc = brick_alloc(bm, &idx);
+    if (rc != UVT_OK) return rc;
+    // re-resolve: growth never moves `chunks`, only the brick pool
+    bm->chunks[pos_to_index(bm->cdim, chx, chy, chz)] = (uint32_t)idx + 1;
+    *out = idx;
+    return UVT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uvt_brickmap_create(uvt_ctx *ctx, uint32_t dim, uvt_brickmap **out) {
+    if (!out || dim == 0 || dim % kChunk != 0) return UVT_ERR_INVALID;
+    uvt_brickmap *bm = new (std::nothrow) uvt_brickmap;
+    if (!bm) return UVT_ERR_OOM;
+    bm->ctx = ctx;
+    bm->dim = dim;
+    bm->cdim = dim / kChunk;
+    const size_t n_chunks = (size_t)bm->cdim * bm->cdim * bm->cdim;
+    const size_t cap = dim;  // GpuBlockAllocator.init(dim): voxel.zig:36
+    if (ctx) {
+        int rc = uvt_world_alloc(ctx, dim, &bm->chunks, &bm->bricks, cap);
+        if (rc != UVT_OK) { delete bm; return rc; }
+    } else {
+        bm->chunks = (uint32_t *)std::calloc(n_chunks, sizeof(uint32_t));
+        bm->bricks = (uint32_t *)std::calloc(cap * kBrickWords, sizeof(uint32_t));
+        if (!bm->chunks || !bm->bricks) { std::free(bm->chunks); std::free(bm->bricks); delete bm; return UVT_ERR_OOM; }
+    }
+    bm->max_block_index = cap;
+    *out = bm;
+    return UVT_OK;
+}
+
+void uvt_brickmap_destroy(uvt_brickmap *bm) {
+    if (!bm) return;
+    if (!bm->ctx) { std::free(bm->chunks); std::free(bm->bricks); }  // ctx staging is owned by the ctx
+    delete bm;
+}
+
+void uvt_brickmap_clear(uvt_brickmap *bm) {
+    const size_t n_chunks = (size_t)bm->cdim * bm->cdim * bm->cdim;
+    std::memset(bm->chunks, 0, n_chunks * sizeof(uint32_t));
+    bm->block_index = 0;
+    std::memset(bm->bricks, 0, bm->max_block_index * kBrickWords * sizeof(uint32_t));
+}
+
+int uvt_brickmap_set(uvt_brickmap *bm, uint32_t x, uint32_t y, uint32_t z, uint32_t voxel) {
+    if (x >= bm->dim || y >= bm->dim || z >= bm->dim) return UVT_ERR_INVALID;  // the reference would index out of bounds
+    size_t blk;
+    int rc = block_for_chunk(bm, x / kChunk, y / kChunk, z / kChunk, &blk);
+    if (rc != UVT_OK) return rc;
+    bm->bricks[blk * kBrickWords + (x % kChunk) + ((y % kChunk) + (z % kChunk) * kChunk) * kChunk] = voxel;
+    return UVT_OK;
+}
+
+uint32_t uvt_brickmap_get(uvt_brickmap *bm, uint32_t x, uint32_t y, uint32_t z) {
+    if (x >= bm->dim || y >= bm->dim || z >= bm->dim) return 0;
+    uint32_t index = bm->chunks[pos_to_index(bm->cdim, x / kChunk, y / kChunk, z / kChunk)];
+    if (index == 0) return 0;
+    return bm->bricks[(size_t)(index - 1) * kBrickWords + (x % kChunk) + ((y % kChunk) + (z % kChunk) * kChunk) * kChunk];
+}
+
+int uvt_brickmap_is_walkable(uvt_brickmap *bm, uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t v = uvt_brickmap_get(bm, x, y, z);
+    return ((v & UVT_VOXEL_SOLID) == 0) || v == 0;
+}
+
+uint32_t uvt_brickmap_dim(const uvt_brickmap *bm) { return bm->dim; }
+size_t uvt_brickmap_n_bricks(const uvt_brickmap *bm) { return bm->block_index; }
+size_t uvt_brickmap_capacity(const uvt_brickmap *bm) { return bm->max_block_index; }
+const uint32_t *uvt_brickmap_chunks(const uvt_brickmap *bm) { return bm->chunks; }
+const uint32_t *uvt_brickmap_bricks(const uvt_brickmap *bm) { return bm->bricks; }
+
+int uvt_brickmap_bind(uvt_brickmap *bm) {
+    if (!bm->ctx) return UVT_ERR_INVALID;
+    return uvt_world_commit(bm->ctx, bm->block_index);
+}
+
+int uvt_brickmap_save(const uvt_brickmap *bm, const char *path) {
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return UVT_ERR_IO;
+    const uint32_t hdr[4] = {0x57545655u /* "UVTW" */, 1u, bm->dim, (uint32_t)bm->block_index};
+    const size_t n_chunks = (size_t)bm->cdim * bm->cdim * bm->cdim;
+    bool ok = std::fwrite(hdr, sizeof hdr, 1, f) == 1 &&
+              std::fwrite(bm->chunks, sizeof(uint32_t), n_chunks, f) == n_chunks &&
+              std::fwrite(bm->bricks, sizeof(uint32_t) * kBrickWords, bm->block_index, f) == bm->block_index;
+    std::fclose(f);
+    return ok ? UVT_OK : UVT_ERR_IO;
+}
+
+int uvt_brickmap_load(uvt_ctx *ctx, const char *path, uvt_brickmap **out) {
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return UVT_ERR_IO;
+    uint32_t hdr[4];
+    if (std::fread(hdr, sizeof hdr, 1, f) != 1 || hdr[0] != 0x57545655u || hdr[1] != 1u) { std::fclose(f); return UVT_ERR_FORMAT; }
+    uvt_brickmap *bm = nullptr;
+    int rc = uvt_brickmap_create(ctx, hdr[2], &bm);
+    if (rc != UVT_OK) { std::fclose(f); return rc; }
+    const size_t n_chunks = (size_t)bm->cdim * bm->cdim * bm->cdim;
+    const size_t n_bricks = hdr[3];
+    while (bm->max_block_index < n_bricks) {  // grow exactly like the allocator would
+        bm->block_index = bm->max_block_index;
+        size_t dummy;
+        rc = brick_alloc(bm, &dummy);
+        if (rc != UVT_OK) { std::fclose(f); uvt_brickmap_destroy(bm); return rc; }
+    }
+    bool ok = std::fread(bm->chunks, sizeof(uint32_t), n_chunks, f) == n_chunks &&
+              std::fread(bm->bricks, sizeof(uint32_t) * kBrickWords, n_bricks, f) == n_bricks;
+    std::fclose(f);
+    if (!ok) { uvt_brickmap_destroy(bm); return UVT_ERR_FORMAT; }
+    bm->block_index = n_bricks;
+    *out = bm;
+    return UVT_OK;
+}
+
+// ---- procgen: src/procgen.zig:6-70 -----------------------------------------------------
+
+uint32_t uvt_procgen_height(uint32_t dim, uint32_t x, uint32_t z, float offset_x, float offset_y) {
+    // procgen.zig:23-24: noise2((offX + x)/10, (offY + z)/10); vh = u32(max(val * dim * 0.1, 0))
+    const float val = uvt_noise2_fbm((offset_x + (float)x) / 10.0f, (offset_y + (float)z) / 10.0f);
+    const float h = std::max(val * (float)dim * 0.1f, 0.0f);
+    return (uint32_t)h;
+}
+
+// place_tree: procgen.zig:55-70
+static int place_tree(uvt_lcg *lcg, uvt_brickmap *w, uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t trunk_height = uvt_lcg_rand(lcg) % 4 + 4;
+    int rc = uvt_brickmap_set(w, x + 1, y, z + 1, uvt_voxel(15, 1));
+    for (uint32_t off = 0; off < trunk_height && rc == UVT_OK; ++off)
+        rc = uvt_brickmap_set(w, x + 1, y + off, z + 1, uvt_voxel(14 + uvt_lcg_rand(lcg) % 3, 1));
+    for (uint32_t a = 0; a < 3; ++a)
+        for (uint32_t b = 0; b < 3; ++b)
+            for (uint32_t c = 0; c < 3 && rc == UVT_OK; ++c)
+                rc = uvt_brickmap_set(w, x + a, y + trunk_height + b, z + c, uvt_voxel(18 + uvt_lcg_rand(lcg) % 2, 1));
+    return rc;
+}
+
+int uvt_procgen(uvt_brickmap *world, uint32_t dim, float offset_x, float offset_y) {
+    if (!world || dim != world->dim) return UVT_ERR_INVALID;
+    uvt_lcg lcg{0x46AE4F};
+    int rc = UVT_OK;
+
+    // water slab (procgen.zig:10-19)
+    for (uint32_t x = 0; x < dim; ++x)
+        for (uint32_t z = 0; z < dim; ++z)
+            for (uint32_t y = 0; y < 16; ++y)
+                if ((rc = uvt_brickmap_set(world, x, y, z, uvt_voxel(13, 1))) != UVT_OK) return rc;
+
+    for (uint32_t x = 0; x < dim; ++x) {
+        for (uint32_t z = 0; z < dim; ++z) {
+            const uint32_t vh = uvt_procgen_height(dim, x, z, offset_x, offset_y);
+
+            for (uint32_t h = 0; h < vh; ++h) {
+                if ((rc = uvt_brickmap_set(world, x, h, z, uvt_voxel(21 + uvt_lcg_rand(&lcg) % 3, 1))) != UVT_OK) return rc;
+                if (h <= 15) {
+                    rc = uvt_brickmap_set(world, x, h, z, uvt_voxel(25 + uvt_lcg_rand(&lcg) % 3, 1));
+                } else if (h == vh - 1 && h > 15) {
+                    rc = uvt_brickmap_set(world, x, h, z, uvt_voxel(uvt_lcg_rand(&lcg) % 6, 1));
+                }
+                if (rc != UVT_OK) return rc;
+            }
+
+            if (vh > 16) {
+                // `continue` at procgen.zig:37-38 also skips the trailing draw
+                if (uvt_brickmap_get(world, x, vh, z) != 0) continue;
+
+                if (uvt_lcg_rand(&lcg) % 5 == 0)
+                    if ((rc = uvt_brickmap_set(world, x, vh, z, uvt_voxel(7 + uvt_lcg_rand(&lcg) % 5, 0))) != UVT_OK) return rc;
+
+                if (uvt_lcg_rand(&lcg) % 71 == 0)
+                    if ((rc = uvt_brickmap_set(world, x, vh, z, uvt_voxel(7 + 5, 1))) != UVT_OK) return rc;
+
+                if (uvt_lcg_rand(&lcg) % 420 == 0 && x < 500 && z < 500 && x > 5 && z > 5)
+                    if ((rc = place_tree(&lcg, world, x, vh, z)) != UVT_OK) return rc;
+            }
+            (void)uvt_lcg_rand(&lcg);
+        }
+    }
+    return UVT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,478 @@
+// kernels.cuh — the three passes of the reference frame (src/game.zig:244-255) as sm_100a
+// kernels: primary (primary.comp.glsl), secondary (secondary.comp.glsl), shade
+// (blit.fragment.glsl), plus the fused frame kernel and small utilities.
+#pragma once
+
+#include "trace.cuh"
+
+namespace uvt {
+
+// camera.glsl:8
+#define UVT_SUN_X 7.52185881e-01f
+#define UVT_SUN_Y 6.58950984e-01f
+#define UVT_SUN_Z 7.52185881e-01f
+
+// Camera as the kernels consume it: camera.glsl:2-6 with tan(fov/2) evaluated once on the host.
+struct CamDev {
+    float pos[3];
+    float tan_half_fov;
+    float mat[16];  // row j = GLSL column j
+};
+
+// Image geometry + multi-GPU row-band partition (uvt_set_partition).
+struct ViewDev {
+    uint32_t W, H;          // full frame
+    uint32_t local_rows;    // rows stored by this ctx
+    uint32_t band_rows, n_parts, part;
+    uint32_t map_dim;
+    uint32_t max_steps;
+    float epsilon;
+    uint32_t entities;
+    // local row -> global row; returns false for padding rows
+    __device__ __forceinline__ bool global_row(uint32_t ly, uint32_t &y) const {
+        if (n_parts == 1u) { y = ly; return ly < H; }
+        const uint32_t lb = ly / band_rows;
+        y = (lb * n_parts + part) * band_rows + (ly - lb * band_rows);
+        return ly < local_rows && y < H;
+    }
+};
+
+struct GBufDev {
+    uint32_t *albedo;   // RGBA8
+    uint32_t *normal;   // RGBA8
+    float4 *position;   // RGBA32F
+    uint32_t *illum;    // RGBA8
+    uint32_t *frame;    // RGBA8
+    uint8_t *hit;       // uvt_hit[...] (28 B each) or nullptr
+    size_t layer_pixels;  // pixels per layer (W * local_rows)
+};
+
+// RGBA8 UNORM store conversion: clamp, *255, +0.5, truncate (0.3 -> 77)
+__device__ __forceinline__ uint32_t unorm8(float c) {
+    if (c != c) return 0u;
+    c = gmin(gmax(c, 0.0f), 1.0f);
+    return __float2uint_rz(c * 255.0f + 0.5f);
+}
+__device__ __forceinline__ uint32_t pack_rgba8(float r, float g, float b, float a) {
+    return unorm8(r) | (unorm8(g) << 8) | (unorm8(b) << 16) | (unorm8(a) << 24);
+}
+
+// SkyDome2: camera.glsl:11-19 (rgb; alpha is 1).  pow(sun, 8) and pow(sun, 3) are integer
+// powers evaluated by multiplication (within the 1/255 shading tolerance of the oracle's powf).
+__device__ __forceinline__ void sky_dome2(float rx, float ry, float rz, float &r, float &g, float &b) {
+    const float sl = sqrtf(UVT_SUN_X * UVT_SUN_X + UVT_SUN_Y * UVT_SUN_Y + UVT_SUN_Z * UVT_SUN_Z);
+    const float rl = sqrtf(rx * rx + ry * ry + rz * rz);
+    const float dot = (UVT_SUN_X / sl) * (rx / rl) + (UVT_SUN_Y / sl) * (ry / rl) + (UVT_SUN_Z / sl) * (rz / rl);
+    const float sun = gmin(gmax(dot, 0.0f), 1.2f);
+    const float s2 = sun * sun, s4 = s2 * s2, p8 = s4 * s4, p3 = s2 * sun;
+    const float k = ry * 0.2f;
+    r = 0.6f - k * 1.0f + 0.15f * 0.5f;
+    g = 0.71f - k * 0.5f + 0.15f * 0.5f;
+    b = 0.75f - k * 1.0f + 0.15f * 0.5f;
+    r += 0.4f * 1.0f * p8; g += 0.4f * 0.6f * p8; b += 0.4f * 0.1f * p8;
+    r += 0.2f * p3; g += 0.08f * p3; b += 0.04f * p3;
+}
+
+// intersectAABB: map.glsl:21-29
+__device__ __forceinline__ void intersect_aabb(float ox, float oy, float oz, float dx, float dy, float dz,
+                                               float lx, float ly, float lz, float hx, float hy, float hz,
+                                               float &t_near, float &t_far) {
+    const float ax = (lx - ox) / dx, bx = (hx - ox) / dx;
+    const float ay = (ly - oy) / dy, by = (hy - oy) / dy;
+    const float az = (lz - oz) / dz, bz = (hz - oz) / dz;
+    t_near = gmax(gmax(gmin(ax, bx), gmin(ay, by)), gmin(az, bz));
+    t_far = gmin(gmin(gmax(ax, bx), gmax(ay, by)), gmax(az, bz));
+}
+
+// traceEntities live part: map.glsl:172-201
+__device__ __forceinline__ bool trace_entities(float ox, float oy, float oz, float dx, float dy, float dz, float max_distance) {
+    const float P[5][3] = {{256.f, 21.f, 256.f}, {251.f, 21.f, 259.f}, {253.f, 21.f, 256.f}, {251.f, 21.f, 256.f}, {257.f, 21.f, 261.f}};
+    float prev_d = __int_as_float(0x7f800000);
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float ex = ox - P[i][0], ey = oy - P[i][1], ez = oz - P[i][2];
+        const float dist = sqrtf(ex * ex + ey * ey + ez * ez);
+        if (dist >= max_distance) continue;
+        float tn, tf;
+        intersect_aabb(ox, oy, oz, dx, dy, dz, P[i][0], P[i][1], P[i][2], P[i][0] + 1.0f, P[i][1] + 1.0f, P[i][2] + 1.0f, tn, tf);
+        if (tf >= tn && prev_d >= tf) {  // the re-test at :197-199 repeats this box's own tf >= tn
+            any = true;
+            prev_d = tf;
+        }
+    }
+    return any;
+}
+
+// primary.comp.glsl:31-43: camera ray and the traceMap start point
+__device__ __forceinline__ void primary_ray(const CamDev &cam, const ViewDev &v, uint32_t px, uint32_t py,
+                                            float &dx, float &dy, float &dz, float &sx, float &sy, float &sz) {
+    float ux = (float)px / (float)v.W * 2.0f - 1.0f;
+    float uy = (float)py / (float)v.H * 2.0f - 1.0f;
+    uy *= (float)v.H / (float)v.W;
+    ux *= cam.tan_half_fov;
+    uy *= cam.tan_half_fov;
+    float q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float acc = cam.mat[0 * 4 + i] * ux;
+        acc = acc + cam.mat[1 * 4 + i] * uy;
+        acc = acc + cam.mat[2 * 4 + i] * 1.0f;
+        acc = acc + cam.mat[3 * 4 + i] * 1.0f;
+        q[i] = acc;
+    }
+    const float len = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    dx = q[0] / len; dy = q[1] / len; dz = q[2] / len;
+    const float D = (float)v.map_dim;
+    float tn, tf;
+    intersect_aabb(cam.pos[0], cam.pos[1], cam.pos[2], dx, dy, dz, 0.0f, 0.0f, 0.0f, D, D, D, tn, tf);
+    const float t0 = gmax(tn, 0.0f);
+    sx = cam.pos[0] + dx * t0 - v.epsilon;
+    sy = cam.pos[1] + dy * t0 - v.epsilon;
+    sz = cam.pos[2] + dz * t0 - v.epsilon;
+}
+
+// packed uvt_hit record (28 B): 7 words
+__device__ __forceinline__ void store_hit(uint8_t *hit_base, size_t i, const Hit &h, float distance) {
+    uint32_t *p = reinterpret_cast<uint32_t *>(hit_base + i * 28u);
+    p[0] = h.px; p[1] = h.py; p[2] = h.pz;
+    p[3] = h.block;
+    p[4] = h.data;
+    p[5] = __float_as_uint(distance);
+    p[6] = (h.trips & 0xFFFFu) | ((h.face & 0xFFu) << 16) | ((h.exit_kind & 0xFFu) << 24);
+}
+
+__device__ __forceinline__ uint32_t normal_rgba8(uint32_t face) {
+    // normals[face-1] stored to RGBA8 UNORM: negative components clamp to 0, alpha = 255
+    // faces 2,4,6 are +x,+y,+z; faces 1,3,5 store (0,0,0,255)
+    uint32_t n = 0xFF000000u;
+    if (face == 2u) n |= 0x000000FFu;
+    if (face == 4u) n |= 0x0000FF00u;
+    if (face == 6u) n |= 0x00FF0000u;
+    return n;
+}
+
+struct DevCounters {
+    unsigned long long rays, t_in, t_chunk, t_block, hits, early_out;
+};
+
+__device__ __forceinline__ void warp_add(unsigned long long *dst, uint32_t v) {
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+}
+
+// CTA tile: 128 threads = 4 warps; a warp covers 8x4 pixels, the CTA 16x8.
+constexpr int kTileW = 16, kTileH = 8, kThreads = 128;
+
+__device__ __forceinline__ void tile_pixel(uint32_t &x, uint32_t &ly) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    x = blockIdx.x * kTileW + (warp & 1u) * 8u + (lane & 7u);
+    ly = blockIdx.y * kTileH + (warp >> 1) * 4u + (lane >> 3);
+}
+
+__device__ __forceinline__ void stage_masks(uint32_t *smem, const uint32_t *__restrict__ gmasks) {
+    for (uint32_t i = threadIdx.x; i < 256u * 16u; i += blockDim.x) smem[i] = __ldg(&gmasks[i]);
+    __syncthreads();
+}
+
+template <class World>
+struct WorldArgs;
+
+template <>
+struct WorldArgs<WorldRef> {
+    WorldRef w;
+    const uint32_t *masks;  // unused
+};
+template <>
+struct WorldArgs<WorldCompact> {
+    WorldCompact w;
+    const uint32_t *masks;  // global [256][16]
+};
+
+// ---- primary pass ------------------------------------------------------------------------
+template <class World, bool COUNT, bool HITBUF>
+__global__ void __launch_bounds__(kThreads) primary_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0,
+                                                           ViewDev v, GBufDev gb, DevCounters *counters) {
+    __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
+    World w = wa.w;
+    if constexpr (std::is_same<World, WorldCompact>::value) {
+        stage_masks(s_masks, wa.masks);
+        w.smem_masks = s_masks;
+    }
+    uint32_t x, ly, y;
+    tile_pixel(x, ly);
+    const bool valid = v.global_row(ly, y) && x < v.W;
+    const CamDev &cam = cams ? cams[blockIdx.z] : cam0;
+
+    TripCounts tc = {0, 0, 0};
+    uint32_t is_hit = 0;
+    if (valid) {
+        float dx, dy, dz, sx, sy, sz;
+        primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
+        Hit h;
+        trace_map<World, COUNT>(w, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+        const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
+        float dist = -1.0f;
+        if (h.data != 0) {  // primary.comp.glsl:58-62
+            is_hit = 1;
+            gb.albedo[i] = h.data;
+            gb.normal[i] = normal_rgba8(h.face);
+            gb.position[i] = make_float4(ceilf(h.hx) / 8.0f, ceilf(h.hy) / 8.0f, ceilf(h.hz) / 8.0f, 1.0f);
+            if (HITBUF) {
+                const float ex = h.hx / 8.0f - cam.pos[0], ey = h.hy / 8.0f - cam.pos[1], ez = h.hz / 8.0f - cam.pos[2];
+                dist = sqrtf(ex * ex + ey * ey + ez * ez);
+            }
+        } else {  // :63-68
+            float r, g, b;
+            sky_dome2(dx, dy, dz, r, g, b);
+            gb.albedo[i] = pack_rgba8(r, g, b, 1.0f);
+            gb.normal[i] = 0xFFFFFFFFu;
+            gb.position[i] = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+        }
+        if (HITBUF) store_hit(gb.hit, i, h, dist);
+    }
+    if (COUNT) {
+        warp_add(&counters->rays, valid ? 1u : 0u);
+        warp_add(&counters->t_in, tc.t_in);
+        warp_add(&counters->t_chunk, tc.t_chunk);
+        warp_add(&counters->t_block, tc.t_block);
+        warp_add(&counters->hits, is_hit);
+    }
+}
+
+// shadow ray of one pixel: secondary.comp.glsl:36-50.  Returns the illumination texel.
+template <class World, bool COUNT>
+__device__ __forceinline__ uint32_t shadow_pixel(const World &w, const ViewDev &v, float posx, float posy, float posz,
+                                                 uint32_t normal, TripCounts &tc, uint32_t &hit) {
+    const float nx = (float)(normal & 255u) / 255.0f, ny = (float)((normal >> 8) & 255u) / 255.0f,
+                nz = (float)((normal >> 16) & 255u) / 255.0f;
+    const float ox = posx + nx * 0.001f, oy = posy + ny * 0.001f, oz = posz + nz * 0.001f;
+    Hit h;
+    trace_map<World, COUNT>(w, ox, oy, oz, UVT_SUN_X, UVT_SUN_Y, UVT_SUN_Z, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+    hit = h.data != 0;
+    bool shadowed = h.data != 0;
+    if (v.entities && !shadowed) {  // an entity hit only matters when the terrain ray missed (same -0.3 either way)
+        const float ex = ox - h.hx / 8.0f, ey = oy - h.hy / 8.0f, ez = oz - h.hz / 8.0f;
+        shadowed = trace_entities(ox, oy, oz, UVT_SUN_X, UVT_SUN_Y, UVT_SUN_Z, sqrtf(ex * ex + ey * ey + ez * ez));
+    }
+    // vec4(SUN_DIR, -/+0.3) -> RGBA8: (192,168,192,0) or (192,168,192,77)
+    return pack_rgba8(UVT_SUN_X, UVT_SUN_Y, UVT_SUN_Z, shadowed ? -0.3f : 0.3f);
+}
+
+// ---- secondary pass ------------------------------------------------------------------------
+template <class World, bool COUNT>
+__global__ void __launch_bounds__(kThreads) secondary_kernel(WorldArgs<World> wa, ViewDev v, GBufDev gb, DevCounters *counters) {
+    __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
+    World w = wa.w;
+    if constexpr (std::is_same<World, WorldCompact>::value) {
+        stage_masks(s_masks, wa.masks);
+        w.smem_masks = s_masks;
+    }
+    uint32_t x, ly, y;
+    tile_pixel(x, ly);
+    const bool valid = v.global_row(ly, y) && x < v.W;
+    TripCounts tc = {0, 0, 0};
+    uint32_t traced = 0, early = 0, hit = 0;
+    if (valid) {
+        const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
+        const float4 pos = gb.position[i];
+        if (pos.x < 0.0f || pos.y < 0.0f || pos.z < 0.0f) {  // :26-29
+            gb.illum[i] = 0u;
+            early = 1;
+        } else {
+            traced = 1;
+            gb.illum[i] = shadow_pixel<World, COUNT>(w, v, pos.x, pos.y, pos.z, gb.normal[i], tc, hit);
+        }
+    }
+    if (COUNT) {
+        warp_add(&counters->rays, traced);
+        warp_add(&counters->t_in, tc.t_in);
+        warp_add(&counters->t_chunk, tc.t_chunk);
+        warp_add(&counters->t_block, tc.t_block);
+        warp_add(&counters->hits, hit);
+        warp_add(&counters->early_out, early);
+    }
+}
+
+// blit.fragment.glsl:23-36 for one pixel
+__device__ __forceinline__ uint32_t shade_pixel(const ViewDev &v, uint32_t x, uint32_t y, uint32_t albedo, uint32_t illum) {
+    const float tx = ((float)x + 0.5f) / (float)v.W, ty = ((float)y + 0.5f) / (float)v.H;
+    float c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = (float)((albedo >> (8 * k)) & 255u) / 255.0f;
+    if (illum != 0u) {
+        const float ir = (float)(illum & 255u) / 255.0f, ig = (float)((illum >> 8) & 255u) / 255.0f,
+                    ib = (float)((illum >> 16) & 255u) / 255.0f, ia = (float)(illum >> 24) / 255.0f;
+        float r, g, b;
+        sky_dome2(ir, ig, ib, r, g, b);
+        c[0] = c[0] + ia * r; c[1] = c[1] + ia * g; c[2] = c[2] + ia * b; c[3] = c[3] + ia * 1.0f;
+    }
+    const float cx = tx - 0.5f, cy = ty - 0.5f;
+    if (sqrtf(cx * cx + cy * cy) <= 0.002f) {
+        c[0] = c[0] * 0.5f + 1.0f * 0.5f; c[1] = c[1] * 0.5f + 1.0f * 0.5f;
+        c[2] = c[2] * 0.5f + 1.0f * 0.5f; c[3] = c[3] * 0.5f + 0.4f * 0.5f;
+    }
+    const float vx = tx * (1.0f - tx), vy = ty * (1.0f - ty);
+    const float grad = powf(vx * vy * 15.0f, 0.6f * 0.3f);
+    return pack_rgba8(grad * c[0], grad * c[1], grad * c[2], grad * c[3]);
+}
+
+// Frame target: either the ctx's own compact band buffer or caller memory (possibly a
+// peer-mapped pointer on another GPU) addressed by GLOBAL row.
+struct FrameTarget {
+    uint32_t *ptr;
+    uint32_t global_rows;  // 1: index by global row y (full-frame target); 0: by local row
+};
+
+__global__ void __launch_bounds__(256) shade_kernel(ViewDev v, GBufDev gb, FrameTarget ft) {
+    const uint32_t x = blockIdx.x * 64u + (threadIdx.x & 63u);
+    const uint32_t ly = blockIdx.y * 4u + (threadIdx.x >> 6);
+    uint32_t y;
+    if (!v.global_row(ly, y) || x >= v.W) return;
+    const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
+    const uint32_t out = shade_pixel(v, x, y, gb.albedo[i], gb.illum[i]);
+    if (ft.global_rows) ft.ptr[(size_t)y * v.W + x] = out;
+    else ft.ptr[i] = out;
+}
+
+// ---- fused frame: primary + secondary + shade in one launch -------------------------------
+// Results are identical to the three separate passes: the shadow ray starts from the same
+// quantised position/normal the G-buffer would hold.
+template <class World, bool GBUF>
+__global__ void __launch_bounds__(kThreads) frame_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0, ViewDev v,
+                                                         uint32_t shadow_steps, GBufDev gb, FrameTarget ft) {
+    __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
+    World w = wa.w;
+    if constexpr (std::is_same<World, WorldCompact>::value) {
+        stage_masks(s_masks, wa.masks);
+        w.smem_masks = s_masks;
+    }
+    uint32_t x, ly, y;
+    tile_pixel(x, ly);
+    if (!(v.global_row(ly, y) && x < v.W)) return;
+    const CamDev &cam = cams ? cams[blockIdx.z] : cam0;
+    float dx, dy, dz, sx, sy, sz;
+    primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
+    Hit h;
+    TripCounts tc;
+    trace_map<World, false>(w, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+    const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
+    uint32_t albedo, normal, illum = 0u;
+    float4 pos;
+    if (h.data != 0) {
+        albedo = h.data;
+        normal = normal_rgba8(h.face);
+        pos = make_float4(ceilf(h.hx) / 8.0f, ceilf(h.hy) / 8.0f, ceilf(h.hz) / 8.0f, 1.0f);
+    } else {
+        float r, g, b;
+        sky_dome2(dx, dy, dz, r, g, b);
+        albedo = pack_rgba8(r, g, b, 1.0f);
+        normal = 0xFFFFFFFFu;
+        pos = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+    }
+    if (!(pos.x < 0.0f || pos.y < 0.0f || pos.z < 0.0f)) {
+        ViewDev vs = v;
+        vs.max_steps = shadow_steps;
+        uint32_t hit;
+        illum = shadow_pixel<World, false>(w, vs, pos.x, pos.y, pos.z, normal, tc, hit);
+    }
+    if (GBUF) {
+        gb.albedo[i] = albedo;
+        gb.normal[i] = normal;
+        gb.position[i] = pos;
+        gb.illum[i] = illum;
+    }
+    const uint32_t out = shade_pixel(v, x, y, albedo, illum);
+    if (ft.global_rows) ft.ptr[(size_t)y * v.W + x] = out;
+    else ft.ptr[i] = out;
+}
+
+// terrain_edit.comp.glsl:10-17: the centre pick ray (rayUV = 0)
+template <class World>
+__global__ void pick_kernel(WorldArgs<World> wa, CamDev cam, ViewDev v, uint8_t *out_hit) {
+    __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
+    World w = wa.w;
+    if constexpr (std::is_same<World, WorldCompact>::value) {
+        stage_masks(s_masks, wa.masks);
+        w.smem_masks = s_masks;
+    }
+    if (threadIdx.x != 0) return;
+    float q[4];
+    for (int i = 0; i < 4; ++i) {
+        float acc = cam.mat[0 * 4 + i] * 0.0f;
+        acc = acc + cam.mat[1 * 4 + i] * 0.0f;
+        acc = acc + cam.mat[2 * 4 + i] * 1.0f;
+        acc = acc + cam.mat[3 * 4 + i] * 1.0f;
+        q[i] = acc;
+    }
+    const float len = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float dx = q[0] / len, dy = q[1] / len, dz = q[2] / len;
+    const float D = (float)v.map_dim;
+    float tn, tf;
+    intersect_aabb(cam.pos[0], cam.pos[1], cam.pos[2], dx, dy, dz, 0.0f, 0.0f, 0.0f, D, D, D, tn, tf);
+    const float t0 = gmax(tn, 0.0f);
+    Hit h;
+    TripCounts tc;
+    trace_map<World, false>(w, cam.pos[0] + dx * t0 - v.epsilon, cam.pos[1] + dy * t0 - v.epsilon, cam.pos[2] + dz * t0 - v.epsilon,
+                            dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+    float dist = -1.0f;
+    if (h.data != 0) {
+        const float ex = h.hx / 8.0f - cam.pos[0], ey = h.hy / 8.0f - cam.pos[1], ez = h.hz / 8.0f - cam.pos[2];
+        dist = sqrtf(ex * ex + ey * ey + ez * ez);
+    }
+    store_hit(out_hit, 0, h, dist);
+}
+
+// ---- world repack: reference u32 bricks -> 8-bit material bricks ---------------------------
+// mat_lut maps a block word to its material id through a small open-addressed table built on the host.
+__global__ void repack_bricks_kernel(const uint32_t *__restrict__ bricks, uint8_t *__restrict__ bricks8, size_t n_words,
+                                     const uint32_t *__restrict__ lut_keys, const uint8_t *__restrict__ lut_vals, uint32_t lut_mask) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4u;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4u; i < n_words; i += stride) {
+        const uint4 wv = *reinterpret_cast<const uint4 *>(bricks + i);
+        const uint32_t wds[4] = {wv.x, wv.y, wv.z, wv.w};
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t m = 0;
+            if (wds[k] != 0) {
+                uint32_t hsh = (wds[k] * 2654435761u) & lut_mask;
+                while (lut_keys[hsh] != wds[k]) hsh = (hsh + 1u) & lut_mask;  // every word present was inserted by the host
+                m = lut_vals[hsh];
+            }
+            packed |= m << (8 * k);
+        }
+        *reinterpret_cast<uint32_t *>(bricks8 + i) = packed;
+    }
+}
+
+// ---- bandwidth probes (roofline denominators) ----------------------------------
+__global__ void __launch_bounds__(256) l2_read_kernel(const uint4 *__restrict__ buf, size_t n_vec, int repeats, uint32_t *sink) {
+    uint32_t acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < repeats; ++r) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+            const uint4 q = __ldcg(buf + i);  // cache-global: bypass L1 so every load is served by L2
+            acc += q.x ^ q.y ^ q.z ^ q.w;
+        }
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n_vec) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) dst[i] = src[i];
+}
+
+// assemble interleaved row bands gathered from n_parts ranks into one frame (rank 0, after the NCCL gather)
+__global__ void __launch_bounds__(256) deinterleave_kernel(const uint32_t *__restrict__ gathered, uint32_t *__restrict__ frame,
+                                                           uint32_t W, uint32_t H, uint32_t band_rows, uint32_t n_parts, uint32_t rows_per_part) {
+    const uint32_t x = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const uint32_t b = y / band_rows, part = b % n_parts, lb = b / n_parts;
+    const uint32_t ly = lb * band_rows + (y - b * band_rows);
+    frame[(size_t)y * W + x] = gathered[((size_t)part * rows_per_part + ly) * W + x];
+}
+
+}  // namespace uvt

@@ -1,0 +1,195 @@
+// trace.cuh — device-side traversal of the two-level voxel world (sm_100a).
+//
+// Semantics follow assets/shaders/map.glsl:83-168 (traceMap) trip for trip: the step
+// SEQUENCE is part of the observable result (the fp32 residual `within` accumulates
+// rounding along the path and the iteration cap counts loop trips), so the freedom taken
+// here is only in WHAT IS FETCHED per trip and how rays are scheduled — never in which
+// steps are taken.  Compile with --fmad=false: every fp32 op is individually rounded.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace uvt {
+
+// GLSL 4.50 §8.3 min/max (NaN behaviour differs from fminf/fmaxf)
+__device__ __forceinline__ float gmin(float x, float y) { return y < x ? y : x; }
+__device__ __forceinline__ float gmax(float x, float y) { return x < y ? y : x; }
+
+struct Hit {
+    uint32_t data;     // HitInfo.data (colour), 0 = miss
+    float hx, hy, hz;  // HitInfo.hit_pos, sub-voxel units
+    uint32_t px, py, pz;
+    uint32_t block;
+    uint32_t face;     // 1..6
+    uint32_t trips;
+    uint32_t exit_kind;  // 0 hit, 1 cap, 2 left the map
+};
+
+struct TripCounts {
+    uint32_t t_in, t_chunk, t_block;
+};
+
+// ---- world views ---------------------------------------------------------------------
+
+// The reference SSBO layout read verbatim (map.glsl:31-47,57-60): u32 chunk table,
+// u32[512] bricks, RGBA8 models addressed by slot (= mdl & 32767, the 32x32x32 slot grid).
+struct WorldRef {
+    const uint32_t *__restrict__ chunks;
+    const uint32_t *__restrict__ bricks;
+    const uint32_t *__restrict__ models;  // [n_slots][512]
+    uint32_t cd;                          // chunks per axis
+    uint32_t n_slots;
+
+    // returns the block word; `chunk_hit` reports chunk entry != 0
+    __device__ __forceinline__ uint32_t block_at(uint32_t px, uint32_t py, uint32_t pz, bool &chunk_hit) const {
+        const uint32_t bx = px >> 3, by = py >> 3, bz = pz >> 3;
+        const uint32_t cx = bx >> 3, cy = by >> 3, cz = bz >> 3;
+        chunk_hit = false;
+        if (cx >= cd || cy >= cd || cz >= cd) return 0;  // unsigned compare covers < 0
+        const uint32_t idx = __ldg(&chunks[cx + cd * (cy + cz * cd)]);
+        if (idx == 0) return 0;
+        chunk_hit = true;
+        return __ldg(&bricks[(size_t)(idx - 1) * 512u + (bx & 7u) + (((bz & 7u) << 3) + (by & 7u)) * 8u]);
+    }
+    // returns the atlas texel (0 = empty sub-voxel)
+    __device__ __forceinline__ uint32_t sub_at(uint32_t block, uint32_t px, uint32_t py, uint32_t pz) const {
+        const uint32_t slot = block & 32767u;
+        if (slot >= n_slots) return 0;
+        return __ldg(&models[slot * 512u + (px & 7u) + ((py & 7u) << 3) + ((pz & 7u) << 6)]);
+    }
+    __device__ __forceinline__ bool sub_solid(uint32_t block, uint32_t px, uint32_t py, uint32_t pz, uint32_t &color) const {
+        color = sub_at(block, px, py, pz);
+        return color != 0;
+    }
+    __device__ __forceinline__ uint32_t block_word(uint32_t block) const { return block; }
+};
+
+// B200 layout (DESIGN.md "Data layout in HBM"): u32 chunk table, 8-bit material bricks
+// (512 B instead of 2 KiB), per-material 512-bit sub-voxel occupancy masks staged in shared
+// memory, colours and block words resolved only at the hit.
+struct WorldCompact {
+    const uint32_t *__restrict__ chunks;
+    const uint8_t *__restrict__ bricks8;    // [n_bricks][512], value = material id (0 = empty)
+    const uint32_t *__restrict__ mat_word;  // [256] material id -> block word
+    const uint32_t *__restrict__ mat_color; // [256][512] material id -> model texels
+    const uint32_t *smem_masks;             // [256][16] shared-memory copy of the occupancy masks
+    uint32_t cd;
+
+    __device__ __forceinline__ uint32_t block_at(uint32_t px, uint32_t py, uint32_t pz, bool &chunk_hit) const {
+        const uint32_t bx = px >> 3, by = py >> 3, bz = pz >> 3;
+        const uint32_t cx = bx >> 3, cy = by >> 3, cz = bz >> 3;
+        chunk_hit = false;
+        if (cx >= cd || cy >= cd || cz >= cd) return 0;
+        const uint32_t idx = __ldg(&chunks[cx + cd * (cy + cz * cd)]);
+        if (idx == 0) return 0;
+        chunk_hit = true;
+        return __ldg(&bricks8[(size_t)(idx - 1) * 512u + (bx & 7u) + (((bz & 7u) << 3) + (by & 7u)) * 8u]);
+    }
+    __device__ __forceinline__ bool sub_solid(uint32_t mat, uint32_t px, uint32_t py, uint32_t pz, uint32_t &color) const {
+        const uint32_t bit = (px & 7u) + ((py & 7u) << 3) + ((pz & 7u) << 6);
+        const uint32_t word = smem_masks[mat * 16u + (bit >> 5)];
+        if (((word >> (bit & 31u)) & 1u) == 0) return false;
+        color = __ldg(&mat_color[mat * 512u + bit]);
+        return true;
+    }
+    __device__ __forceinline__ uint32_t block_word(uint32_t mat) const { return __ldg(&mat_word[mat]); }
+};
+
+// ---- traceMap ------------------------------------------------------------------------
+// map.glsl:83-168.  `bound` = 8 * MAP_DIMENSION.
+template <class World, bool COUNT>
+__device__ __forceinline__ void trace_map(const World &w, float ox, float oy, float oz, float dx, float dy, float dz,
+                                          int max_steps, int bound, Hit &out, TripCounts &tc) {
+    if (dx == 0.0f) dx = 0.001f;  // :85-90
+    if (dy == 0.0f) dy = 0.001f;
+    if (dz == 0.0f) dz = 0.001f;
+
+    // raySign / rayPositivity / rayInv: :94-96 (no zero components remain)
+    const bool posx = dx > 0.0f, posy = dy > 0.0f, posz = dz > 0.0f;
+    const float invx = 1.0f / dx, invy = 1.0f / dy, invz = 1.0f / dz;
+
+    int mi = 0;  // :98
+    const float o8x = ox * 8.0f, o8y = oy * 8.0f, o8z = oz * 8.0f;
+    int gx = __float2int_rz(o8x), gy = __float2int_rz(o8y), gz = __float2int_rz(o8z);  // :101
+    float wx = o8x - (float)gx, wy = o8y - (float)gy, wz = o8z - (float)gz;             // :102
+    bool big = false;  // stepSize == 3
+
+    out.data = 0;
+    out.hx = out.hy = out.hz = -1.0f;  // :167
+    out.px = out.py = out.pz = 0xFFFFFFFFu;
+    out.block = 0;
+    out.face = 0;
+    out.exit_kind = 1;
+    if (COUNT) tc.t_in = tc.t_chunk = tc.t_block = 0;
+
+    int trip = 0;
+    for (; trip < max_steps; ++trip) {
+        // :107 — one unsigned compare per axis covers both < 0 and >= bound
+        if ((unsigned)gx >= (unsigned)bound || (unsigned)gy >= (unsigned)bound || (unsigned)gz >= (unsigned)bound) {
+            out.exit_kind = 2;
+            break;
+        }
+        if (COUNT) tc.t_in++;
+        const uint32_t px = (uint32_t)gx + __float2uint_rz(wx);  // :108
+        const uint32_t py = (uint32_t)gy + __float2uint_rz(wy);
+        const uint32_t pz = (uint32_t)gz + __float2uint_rz(wz);
+
+        bool chunk_hit;
+        const uint32_t block = w.block_at(px, py, pz, chunk_hit);  // :114
+        if (COUNT && chunk_hit) tc.t_chunk++;
+
+        if (block != 0) {
+            if (COUNT) tc.t_block++;
+            uint32_t color;
+            if (w.sub_solid(block, px, py, pz, color)) {  // :117-118
+                out.data = color;
+                out.face = mi == 0 ? (posx ? 1u : 2u) : (mi == 1 ? (posy ? 3u : 4u) : (posz ? 5u : 6u));  // :119-125
+                out.hx = (float)gx + wx;  // :127
+                out.hy = (float)gy + wy;
+                out.hz = (float)gz + wz;
+                out.px = px; out.py = py; out.pz = pz;
+                out.block = w.block_word(block);
+                out.exit_kind = 0;
+                out.trips = (uint32_t)trip + 1u;
+                return;
+            }
+            if (big) {  // :131-135
+                gx += __float2int_rz(wx);
+                gy += __float2int_rz(wy);
+                gz += __float2int_rz(wz);
+                wx = wx - floorf(wx);
+                wy = wy - floorf(wy);
+                wz = wz - floorf(wz);
+                big = false;
+            }
+        } else if (!big) {  // :140-144
+            wx += (float)(gx & 7);
+            wy += (float)(gy & 7);
+            wz += (float)(gz & 7);
+            gx &= ~7;
+            gy &= ~7;
+            gz &= ~7;
+            big = true;
+        }
+
+        // dda stepping: :157-162
+        const float stepf = big ? 8.0f : 1.0f;
+        const float tx = ((posx ? stepf : 0.0f) - wx) * invx;
+        const float ty = ((posy ? stepf : 0.0f) - wy) * invy;
+        const float tz = ((posz ? stepf : 0.0f) - wz) * invz;
+        mi = tx < ty ? (tx < tz ? 0 : 2) : (ty < tz ? 1 : 2);
+        const float tm = mi == 0 ? tx : (mi == 1 ? ty : tz);
+        const int istep = big ? 8 : 1;
+        wx += dx * tm;
+        wy += dy * tm;
+        wz += dz * tm;
+        const float reset = stepf * 0.999f;  // float((1 - pos) << step) * 0.999f
+        if (mi == 0) { gx += posx ? istep : -istep; wx = posx ? 0.0f : reset; }
+        else if (mi == 1) { gy += posy ? istep : -istep; wy = posy ? 0.0f : reset; }
+        else { gz += posz ? istep : -istep; wz = posz ? 0.0f : reset; }
+    }
+    out.trips = (uint32_t)trip;
+}
+
+}  // namespace uvt

@@ -1,0 +1,899 @@
+// uvt.cu — the C ABI of include/uvt.h: context, device memory, uploads, repack, dispatch.
+//
+// One ctx = one CUDA device + one in-order stream (the reference is one GL context with one
+// in-order queue: src/engine/graphics/shader.zig:113-117).  The host owns world / atlas /
+// camera source data; the ctx owns all device memory and the pinned staging it hands out.
+// There is NO CPU fallback anywhere in this file: every pass is a kernel launch.
+#include "uvt.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace uvt;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct uvt_ctx {
+    uvt_params params;
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    uint64_t launches = 0;
+
+    // ---- world staging (pinned host) and device copies
+    uint32_t dim = 0, cd = 0;
+    uint32_t *h_chunks = nullptr;
+    uint32_t *h_bricks = nullptr;
+    size_t h_capacity = 0;  // bricks
+    size_t n_bricks = 0;    // committed
+    uint32_t *d_chunks = nullptr;
+    uint32_t *d_bricks = nullptr;
+    size_t d_brick_capacity = 0;
+    uint8_t *d_bricks8 = nullptr;
+    size_t d_brick8_capacity = 0;
+    bool world_committed = false;
+
+    // ---- atlas: host copy by slot (slot = x/8 + 32*(y/8) + 1024*(z/8)), device [n_slots][512]
+    std::vector<uint32_t> h_models;
+    uint32_t n_slots = 0;
+    uint32_t *d_models = nullptr;
+    uint32_t d_model_slots = 0;
+    bool atlas_dirty = true;
+
+    // ---- materials (compact layout): id -> block word / colours / occupancy mask
+    std::vector<uint32_t> mat_words;  // index = material id, [0] unused
+    bool materials_dirty = true;
+    bool compact_ok = false;
+    uint32_t *d_mat_word = nullptr;   // [256]
+    uint32_t *d_mat_color = nullptr;  // [256][512]
+    uint32_t *d_mat_mask = nullptr;   // [256][16]
+
+    // ---- cameras
+    std::vector<uvt_camera> cams;
+    CamDev cam0;
+    CamDev *d_cams = nullptr;
+    int d_cams_capacity = 0;
+    bool have_camera = false;
+
+    // ---- G-buffer
+    uint32_t W = 0, H = 0, layers = 1;
+    uint32_t band_rows = 8, n_parts = 1, part = 0, local_rows = 0;
+    uint32_t *d_albedo = nullptr, *d_normal = nullptr, *d_illum = nullptr, *d_frame = nullptr;
+    float4 *d_position = nullptr;
+    uint8_t *d_hit = nullptr;
+    size_t gbuf_pixels = 0;  // allocated pixels (all layers)
+    uint32_t *frame_target = nullptr;
+    bool frame_target_global_rows = false;
+
+    // ---- counters / timing
+    DevCounters *d_counters = nullptr;
+    uint8_t *d_pick = nullptr;
+    bool timing = false;
+    cudaEvent_t ev[4][2] = {};
+    bool ev_valid[4] = {false, false, false, false};
+    uint32_t *d_sink = nullptr;
+};
+
+struct uvt_pipeline {
+    uvt_ctx *ctx;
+    uvt_pipeline_kind kind;
+};
+
+namespace {
+
+int set_error(uvt_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define UVT_CUDA(ctx, expr)                                                                                     \
+    do {                                                                                                        \
+        cudaError_t e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            return set_error((ctx), e_ == cudaErrorMemoryAllocation ? UVT_ERR_OOM : UVT_ERR_CUDA, "%s: %s (%s:%d)", \
+                             #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                                \
+    } while (0)
+
+#define UVT_REQUIRE(ctx, cond, msg)                                  \
+    do {                                                             \
+        if (!(cond)) return set_error((ctx), UVT_ERR_INVALID, "%s", (msg)); \
+    } while (0)
+
+uint32_t compute_local_rows(uint32_t H, uint32_t band_rows, uint32_t n_parts, uint32_t part) {
+    if (n_parts == 1) return H;
+    const uint32_t n_bands = (H + band_rows - 1) / band_rows;
+    // bands part, part + n_parts, ...; all but possibly the globally last band are full
+    uint32_t rows = 0;
+    for (uint32_t b = part; b < n_bands; b += n_parts) rows += std::min(band_rows, H - b * band_rows);
+    return rows;
+}
+
+// local row count including the padding of a ragged last band (storage is band-granular)
+uint32_t storage_rows(uint32_t H, uint32_t band_rows, uint32_t n_parts, uint32_t part) {
+    if (n_parts == 1) return H;
+    const uint32_t n_bands = (H + band_rows - 1) / band_rows;
+    uint32_t bands = 0;
+    for (uint32_t b = part; b < n_bands; b += n_parts) ++bands;
+    return bands * band_rows;
+}
+
+void free_gbuffer(uvt_ctx *c) {
+    cudaFree(c->d_albedo); cudaFree(c->d_normal); cudaFree(c->d_position); cudaFree(c->d_illum);
+    cudaFree(c->d_frame); cudaFree(c->d_hit);
+    c->d_albedo = c->d_normal = c->d_illum = c->d_frame = nullptr;
+    c->d_position = nullptr;
+    c->d_hit = nullptr;
+    c->gbuf_pixels = 0;
+}
+
+int alloc_gbuffer(uvt_ctx *c) {
+    // GBuffer.resize recreates all four textures (gbuffer.zig:18-30)
+    free_gbuffer(c);
+    c->local_rows = compute_local_rows(c->H, c->band_rows, c->n_parts, c->part);
+    const size_t rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
+    const size_t px = (size_t)c->W * rows * c->layers;
+    if (px == 0) return UVT_OK;
+    UVT_CUDA(c, cudaMalloc(&c->d_albedo, px * 4));
+    UVT_CUDA(c, cudaMalloc(&c->d_normal, px * 4));
+    UVT_CUDA(c, cudaMalloc(&c->d_position, px * 16));
+    UVT_CUDA(c, cudaMalloc(&c->d_illum, px * 4));
+    UVT_CUDA(c, cudaMalloc(&c->d_frame, px * 4));
+    if (c->params.flags & UVT_FLAG_HIT_BUFFER) UVT_CUDA(c, cudaMalloc(&c->d_hit, px * sizeof(uvt_hit)));
+    // GL zero-initialises fresh storage
+    UVT_CUDA(c, cudaMemsetAsync(c->d_albedo, 0, px * 4, c->stream));
+    UVT_CUDA(c, cudaMemsetAsync(c->d_normal, 0, px * 4, c->stream));
+    UVT_CUDA(c, cudaMemsetAsync(c->d_position, 0, px * 16, c->stream));
+    UVT_CUDA(c, cudaMemsetAsync(c->d_illum, 0, px * 4, c->stream));
+    UVT_CUDA(c, cudaMemsetAsync(c->d_frame, 0, px * 4, c->stream));
+    c->gbuf_pixels = px;
+    return UVT_OK;
+}
+
+size_t layer_pixels(const uvt_ctx *c) { return (size_t)c->W * storage_rows(c->H, c->band_rows, c->n_parts, c->part); }
+
+void derive_cam(const uvt_camera &in, CamDev &out) {
+    out.pos[0] = in.cam_pos[0]; out.pos[1] = in.cam_pos[1]; out.pos[2] = in.cam_pos[2];
+    out.tan_half_fov = tanf(in.fov / 2.0f);  // primary.comp.glsl:36, evaluated once per frame on the host
+    std::memcpy(out.mat, in.cam_mat, sizeof out.mat);
+}
+
+// Upload the atlas slots and (compact layout) rebuild material tables.
+int ensure_ready(uvt_ctx *c) {
+    UVT_REQUIRE(c, c->world_committed, "no world committed (uvt_world_alloc + uvt_world_commit first)");
+    if (c->atlas_dirty) {
+        const uint32_t slots = std::max<uint32_t>(c->n_slots, 1u);
+        if (slots > c->d_model_slots) {
+            cudaFree(c->d_models);
+            c->d_models = nullptr;
+            UVT_CUDA(c, cudaMalloc(&c->d_models, (size_t)slots * 512 * 4));
+            c->d_model_slots = slots;
+        }
+        if (c->n_slots)
+            UVT_CUDA(c, cudaMemcpyAsync(c->d_models, c->h_models.data(), (size_t)c->n_slots * 512 * 4, cudaMemcpyHostToDevice, c->stream));
+        else
+            UVT_CUDA(c, cudaMemsetAsync(c->d_models, 0, 512 * 4, c->stream));
+        c->atlas_dirty = false;
+        c->materials_dirty = true;
+    }
+    if (c->materials_dirty && c->compact_ok) {
+        std::vector<uint32_t> words(256, 0), colors(256 * 512, 0), masks(256 * 16, 0);
+        for (size_t m = 1; m < c->mat_words.size(); ++m) {
+            words[m] = c->mat_words[m];
+            const uint32_t slot = c->mat_words[m] & 32767u;
+            if (slot >= c->n_slots) continue;  // unloaded model: reads as empty
+            const uint32_t *tex = &c->h_models[(size_t)slot * 512];
+            for (uint32_t b = 0; b < 512; ++b) {
+                colors[m * 512 + b] = tex[b];
+                if (tex[b] != 0) masks[m * 16 + (b >> 5)] |= 1u << (b & 31u);
+            }
+        }
+        UVT_CUDA(c, cudaMemcpyAsync(c->d_mat_word, words.data(), 256 * 4, cudaMemcpyHostToDevice, c->stream));
+        UVT_CUDA(c, cudaMemcpyAsync(c->d_mat_color, colors.data(), 256 * 512 * 4, cudaMemcpyHostToDevice, c->stream));
+        UVT_CUDA(c, cudaMemcpyAsync(c->d_mat_mask, masks.data(), 256 * 16 * 4, cudaMemcpyHostToDevice, c->stream));
+        UVT_CUDA(c, cudaStreamSynchronize(c->stream));  // the staging vectors die at scope exit
+        c->materials_dirty = false;
+    }
+    return UVT_OK;
+}
+
+bool use_compact(const uvt_ctx *c) { return c->params.layout == UVT_LAYOUT_COMPACT && c->compact_ok; }
+
+WorldArgs<WorldRef> world_ref(const uvt_ctx *c) {
+    WorldArgs<WorldRef> a;
+    a.w.chunks = c->d_chunks;
+    a.w.bricks = c->d_bricks;
+    a.w.models = c->d_models;
+    a.w.cd = c->cd;
+    a.w.n_slots = c->n_slots;
+    a.masks = nullptr;
+    return a;
+}
+
+WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
+    WorldArgs<WorldCompact> a;
+    a.w.chunks = c->d_chunks;
+    a.w.bricks8 = c->d_bricks8;
+    a.w.mat_word = c->d_mat_word;
+    a.w.mat_color = c->d_mat_color;
+    a.w.smem_masks = nullptr;
+    a.w.cd = c->cd;
+    a.masks = c->d_mat_mask;
+    return a;
+}
+
+ViewDev make_view(const uvt_ctx *c, uint32_t max_steps) {
+    ViewDev v;
+    v.W = c->W; v.H = c->H;
+    v.local_rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
+    v.band_rows = c->band_rows; v.n_parts = c->n_parts; v.part = c->part;
+    v.map_dim = c->dim;
+    v.max_steps = max_steps;
+    v.epsilon = c->params.epsilon;
+    v.entities = (c->params.flags & UVT_FLAG_ENTITIES) ? 1u : 0u;
+    return v;
+}
+
+GBufDev make_gbuf(const uvt_ctx *c) {
+    GBufDev g;
+    g.albedo = c->d_albedo; g.normal = c->d_normal; g.position = c->d_position; g.illum = c->d_illum;
+    g.frame = c->d_frame; g.hit = c->d_hit;
+    g.layer_pixels = layer_pixels(c);
+    return g;
+}
+
+FrameTarget make_target(const uvt_ctx *c) {
+    FrameTarget t;
+    t.ptr = c->frame_target ? c->frame_target : c->d_frame;
+    t.global_rows = (c->frame_target && c->frame_target_global_rows) ? 1u : 0u;
+    return t;
+}
+
+dim3 trace_grid(const uvt_ctx *c) {
+    const uint32_t rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
+    return dim3((c->W + kTileW - 1) / kTileW, (rows + kTileH - 1) / kTileH, c->layers);
+}
+
+struct PassTimer {
+    uvt_ctx *c;
+    int which;
+    PassTimer(uvt_ctx *ctx, int w) : c(ctx), which(w) {
+        if (c->timing) cudaEventRecord(c->ev[which][0], c->stream);
+    }
+    ~PassTimer() {
+        if (c->timing) {
+            cudaEventRecord(c->ev[which][1], c->stream);
+            c->ev_valid[which] = true;
+        }
+    }
+};
+
+int check_launch(uvt_ctx *c, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    c->launches++;
+    return UVT_OK;
+}
+
+int pre_dispatch(uvt_ctx *c) {
+    UVT_REQUIRE(c, c->W && c->H, "no G-buffer (uvt_resize first)");
+    UVT_REQUIRE(c, c->have_camera, "no camera (uvt_set_camera first)");
+    return ensure_ready(c);
+}
+
+template <bool COUNT>
+int launch_primary(uvt_ctx *c) {
+    const ViewDev v = make_view(c, c->params.primary_max_steps);
+    const GBufDev g = make_gbuf(c);
+    const dim3 grid = trace_grid(c);
+    const CamDev *cams = c->layers > 1 ? c->d_cams : nullptr;
+    const bool hb = c->d_hit != nullptr;
+    if (use_compact(c)) {
+        auto wa = world_compact(c);
+        if (hb) primary_kernel<WorldCompact, COUNT, true><<<grid, kThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters);
+        else primary_kernel<WorldCompact, COUNT, false><<<grid, kThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters);
+    } else {
+        auto wa = world_ref(c);
+        if (hb) primary_kernel<WorldRef, COUNT, true><<<grid, kThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters);
+        else primary_kernel<WorldRef, COUNT, false><<<grid, kThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters);
+    }
+    return check_launch(c, "primary_kernel");
+}
+
+template <bool COUNT>
+int launch_secondary(uvt_ctx *c) {
+    const ViewDev v = make_view(c, c->params.shadow_max_steps);
+    const GBufDev g = make_gbuf(c);
+    const dim3 grid = trace_grid(c);
+    if (use_compact(c)) secondary_kernel<WorldCompact, COUNT><<<grid, kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
+    else secondary_kernel<WorldRef, COUNT><<<grid, kThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
+    return check_launch(c, "secondary_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+void uvt_default_params(uvt_params *p) {
+    std::memset(p, 0, sizeof *p);
+    p->map_dim = 512;
+    p->primary_max_steps = 192;
+    p->shadow_max_steps = 48;
+    p->edit_max_steps = 64;
+    p->epsilon = 0.001f;
+    p->flags = UVT_FLAG_ENTITIES;
+    p->layout = UVT_LAYOUT_COMPACT;
+}
+
+int uvt_abi_version(void) { return UVT_ABI_VERSION; }
+
+int uvt_create(const uvt_params *params, int device, uvt_ctx **out) {
+    if (!out) return set_error(nullptr, UVT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_error(nullptr, UVT_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU path",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return set_error(nullptr, UVT_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return set_error(nullptr, UVT_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return set_error(nullptr, UVT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return set_error(nullptr, UVT_ERR_NO_DEVICE, "device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
+
+    uvt_ctx *c = new uvt_ctx;
+    if (params) c->params = *params;
+    else uvt_default_params(&c->params);
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    auto fail = [&](cudaError_t err, const char *what) {
+        set_error(nullptr, UVT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+        uvt_destroy(c);
+        return UVT_ERR_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    c->stream = c->own_stream;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 2; ++j)
+            if ((e = cudaEventCreate(&c->ev[i][j])) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(&c->d_counters, sizeof(DevCounters))) != cudaSuccess) return fail(e, "cudaMalloc counters");
+    if ((e = cudaMalloc(&c->d_pick, 32)) != cudaSuccess) return fail(e, "cudaMalloc pick");
+    if ((e = cudaMalloc(&c->d_sink, 4)) != cudaSuccess) return fail(e, "cudaMalloc sink");
+    if ((e = cudaMalloc(&c->d_mat_word, 256 * 4)) != cudaSuccess) return fail(e, "cudaMalloc mat_word");
+    if ((e = cudaMalloc(&c->d_mat_color, 256 * 512 * 4)) != cudaSuccess) return fail(e, "cudaMalloc mat_color");
+    if ((e = cudaMalloc(&c->d_mat_mask, 256 * 16 * 4)) != cudaSuccess) return fail(e, "cudaMalloc mat_mask");
+    std::memset(&c->cam0, 0, sizeof c->cam0);
+    *out = c;
+    return UVT_OK;
+}
+
+void uvt_destroy(uvt_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    free_gbuffer(c);
+    cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
+    cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models);
+    cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
+    cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char *uvt_last_error(uvt_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int uvt_set_stream(uvt_ctx *c, void *cuda_stream) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return UVT_OK;
+}
+
+int uvt_get_params(uvt_ctx *c, uvt_params *out) {
+    if (!c || !out) return UVT_ERR_INVALID;
+    *out = c->params;
+    return UVT_OK;
+}
+
+int uvt_set_layout(uvt_ctx *c, uint32_t layout) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, layout == UVT_LAYOUT_COMPACT || layout == UVT_LAYOUT_REFERENCE, "unknown layout");
+    c->params.layout = layout;
+    return UVT_OK;
+}
+
+int uvt_effective_layout(uvt_ctx *c) { return c ? (use_compact(c) ? UVT_LAYOUT_COMPACT : UVT_LAYOUT_REFERENCE) : UVT_ERR_INVALID; }
+
+int uvt_set_max_steps(uvt_ctx *c, uint32_t primary, uint32_t shadow) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, primary <= 65535u && shadow <= 65535u, "step caps must fit 16 bits (uvt_hit.trips)");
+    c->params.primary_max_steps = primary;
+    c->params.shadow_max_steps = shadow;
+    return UVT_OK;
+}
+
+// ---- pipelines -----------------------------------------------------------------------------
+int uvt_pipeline_create(uvt_ctx *c, uvt_pipeline_kind kind, uvt_pipeline **out) {
+    if (!c || !out) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, kind >= UVT_PIPELINE_PRIMARY && kind <= UVT_PIPELINE_BLIT, "unknown pipeline kind");
+    // the analogue of compile + link: make sure the kernel image for this device resolves
+    cudaFuncAttributes fa;
+    const void *fn = nullptr;
+    switch (kind) {
+        case UVT_PIPELINE_PRIMARY: fn = (const void *)primary_kernel<WorldCompact, false, false>; break;
+        case UVT_PIPELINE_SECONDARY: fn = (const void *)secondary_kernel<WorldCompact, false>; break;
+        case UVT_PIPELINE_EDIT: fn = (const void *)pick_kernel<WorldCompact>; break;
+        case UVT_PIPELINE_BLIT: fn = (const void *)shade_kernel; break;
+    }
+    UVT_CUDA(c, cudaFuncGetAttributes(&fa, fn));
+    *out = new uvt_pipeline{c, kind};
+    return UVT_OK;
+}
+
+void uvt_pipeline_destroy(uvt_pipeline *p) { delete p; }
+
+int uvt_pipeline_dispatch(uvt_pipeline *p, uint32_t gx, uint32_t gy, uint32_t gz) {
+    if (!p) return UVT_ERR_INVALID;
+    uvt_ctx *c = p->ctx;
+    if (p->kind == UVT_PIPELINE_BLIT) return uvt_shade(c);  // RasterPipeline.draw(4)
+    if (p->kind == UVT_PIPELINE_EDIT) {
+        UVT_REQUIRE(c, gx == 1 && gy == 1 && gz == 1, "terrain_edit dispatches 1x1x1");
+        uvt_hit h;
+        return uvt_pick(c, &h);
+    }
+    // game.zig:241-242: (W/32 + 1) x (H/32 + 1) x 1 groups of 32x32 threads
+    UVT_REQUIRE(c, gz == 1 && (uint64_t)gx * 32u >= c->W && (uint64_t)gy * 32u >= c->H,
+                "dispatch does not cover the G-buffer (expected (W/32+1) x (H/32+1) x 1 groups)");
+    return p->kind == UVT_PIPELINE_PRIMARY ? uvt_dispatch_primary(c) : uvt_dispatch_secondary(c);
+}
+
+// ---- world ------------------------------------------------------------------------------------
+int uvt_world_alloc(uvt_ctx *c, uint32_t dim, uint32_t **chunks_host, uint32_t **bricks_host, size_t brick_capacity) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, chunks_host && bricks_host, "NULL out pointer");
+    UVT_REQUIRE(c, dim >= 8 && dim % 8 == 0 && dim <= 4096, "dim must be a multiple of 8 in [8, 4096]");
+    UVT_REQUIRE(c, brick_capacity > 0, "brick_capacity must be > 0");
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
+    cudaFree(c->d_chunks);
+    c->h_chunks = c->h_bricks = nullptr;
+    c->d_chunks = nullptr;
+    c->dim = dim;
+    c->cd = dim / 8;
+    c->params.map_dim = dim;
+    const size_t n_chunks = (size_t)c->cd * c->cd * c->cd;
+    UVT_CUDA(c, cudaHostAlloc(&c->h_chunks, n_chunks * 4, cudaHostAllocDefault));
+    UVT_CUDA(c, cudaHostAlloc(&c->h_bricks, brick_capacity * 2048, cudaHostAllocDefault));
+    std::memset(c->h_chunks, 0, n_chunks * 4);              // voxel.zig:34
+    std::memset(c->h_bricks, 0, brick_capacity * 2048);     // GL zero-initialised storage
+    UVT_CUDA(c, cudaMalloc(&c->d_chunks, n_chunks * 4));
+    c->h_capacity = brick_capacity;
+    c->n_bricks = 0;
+    c->world_committed = false;
+    *chunks_host = c->h_chunks;
+    *bricks_host = c->h_bricks;
+    return UVT_OK;
+}
+
+int uvt_world_grow(uvt_ctx *c, size_t new_capacity, uint32_t **bricks_host) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, c->h_bricks && bricks_host, "no world allocated");
+    UVT_REQUIRE(c, new_capacity >= c->h_capacity, "cannot shrink the brick pool (buffer.zig:51-52)");
+    if (new_capacity == c->h_capacity) { *bricks_host = c->h_bricks; return UVT_OK; }
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));  // an upload may still be reading the old staging
+    uint32_t *nb = nullptr;
+    UVT_CUDA(c, cudaHostAlloc(&nb, new_capacity * 2048, cudaHostAllocDefault));
+    std::memcpy(nb, c->h_bricks, c->h_capacity * 2048);  // copyNamedBufferSubData (buffer.zig:57)
+    std::memset((uint8_t *)nb + c->h_capacity * 2048, 0, (new_capacity - c->h_capacity) * 2048);
+    cudaFreeHost(c->h_bricks);
+    c->h_bricks = nb;
+    c->h_capacity = new_capacity;
+    *bricks_host = nb;
+    return UVT_OK;
+}
+
+int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, c->h_chunks && c->h_bricks, "no world allocated");
+    UVT_REQUIRE(c, n_bricks <= c->h_capacity, "n_bricks exceeds the pool capacity");
+    const size_t n_chunks = (size_t)c->cd * c->cd * c->cd;
+    // every chunk entry must name a committed brick
+    // (checked on the host: a bad index would be an out-of-bounds device read)
+    for (size_t i = 0; i < n_chunks; ++i)
+        if (c->h_chunks[i] > n_bricks) return set_error(c, UVT_ERR_INVALID, "chunk entry %zu names brick %u >= n_bricks %zu", i, c->h_chunks[i] - 1, n_bricks);
+
+    const size_t cap = std::max<size_t>(n_bricks, 1);
+    if (cap > c->d_brick_capacity) {
+        cudaFree(c->d_bricks);
+        c->d_bricks = nullptr;
+        const size_t want = std::max(cap, c->h_capacity);
+        UVT_CUDA(c, cudaMalloc(&c->d_bricks, want * 2048));
+        c->d_brick_capacity = want;
+    }
+    UVT_CUDA(c, cudaMemcpyAsync(c->d_chunks, c->h_chunks, n_chunks * 4, cudaMemcpyHostToDevice, c->stream));
+    if (n_bricks) UVT_CUDA(c, cudaMemcpyAsync(c->d_bricks, c->h_bricks, n_bricks * 2048, cudaMemcpyHostToDevice, c->stream));
+
+    // material table: distinct block words in first-appearance order (deterministic)
+    c->mat_words.assign(1, 0u);
+    std::unordered_map<uint32_t, uint32_t> ids;
+    const size_t n_words = n_bricks * 512;
+    bool overflow = false;
+    uint32_t last_word = 0;
+    for (size_t i = 0; i < n_words && !overflow; ++i) {
+        const uint32_t wd = c->h_bricks[i];
+        if (wd == 0 || wd == last_word) continue;
+        last_word = wd;
+        if (ids.find(wd) == ids.end()) {
+            if (c->mat_words.size() >= 256) { overflow = true; break; }
+            ids.emplace(wd, (uint32_t)c->mat_words.size());
+            c->mat_words.push_back(wd);
+        }
+    }
+    c->compact_ok = !overflow;
+    if (c->compact_ok) {
+        if (cap > c->d_brick8_capacity) {
+            cudaFree(c->d_bricks8);
+            c->d_bricks8 = nullptr;
+            const size_t want = std::max(cap, c->h_capacity);
+            UVT_CUDA(c, cudaMalloc(&c->d_bricks8, want * 512));
+            c->d_brick8_capacity = want;
+        }
+        if (n_bricks) {
+            // open-addressed word -> id table for the repack kernel
+            const uint32_t lut_size = 1024, lut_mask = lut_size - 1;
+            std::vector<uint32_t> keys(lut_size, 0);
+            std::vector<uint8_t> vals(lut_size, 0);
+            for (size_t m = 1; m < c->mat_words.size(); ++m) {
+                uint32_t h = (c->mat_words[m] * 2654435761u) & lut_mask;
+                while (keys[h] != 0) h = (h + 1) & lut_mask;
+                keys[h] = c->mat_words[m];
+                vals[h] = (uint8_t)m;
+            }
+            uint32_t *d_keys = nullptr;
+            uint8_t *d_vals = nullptr;
+            UVT_CUDA(c, cudaMalloc(&d_keys, lut_size * 4));
+            UVT_CUDA(c, cudaMalloc(&d_vals, lut_size));
+            UVT_CUDA(c, cudaMemcpyAsync(d_keys, keys.data(), lut_size * 4, cudaMemcpyHostToDevice, c->stream));
+            UVT_CUDA(c, cudaMemcpyAsync(d_vals, vals.data(), lut_size, cudaMemcpyHostToDevice, c->stream));
+            const int blocks = c->sm_count * 8;
+            repack_bricks_kernel<<<blocks, 256, 0, c->stream>>>(c->d_bricks, c->d_bricks8, n_words, d_keys, d_vals, lut_mask);
+            int rc = check_launch(c, "repack_bricks_kernel");
+            cudaStreamSynchronize(c->stream);
+            cudaFree(d_keys);
+            cudaFree(d_vals);
+            if (rc != UVT_OK) return rc;
+        }
+    }
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_bricks = n_bricks;
+    c->world_committed = true;
+    c->materials_dirty = true;
+    return UVT_OK;
+}
+
+// ---- atlas --------------------------------------------------------------------------------------
+int uvt_atlas_upload(uvt_ctx *c, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t w, uint32_t h, uint32_t d, const uint32_t *rgba) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, rgba, "rgba is NULL");
+    UVT_REQUIRE(c, (uint64_t)ox + w <= 256 && (uint64_t)oy + h <= 256 && (uint64_t)oz + d <= 256, "sub-box leaves the 256^3 atlas");
+    for (uint32_t z = 0; z < d; ++z)
+        for (uint32_t y = 0; y < h; ++y)
+            for (uint32_t x = 0; x < w; ++x) {
+                const uint32_t ax = ox + x, ay = oy + y, az = oz + z;
+                const uint32_t slot = (ax >> 3) + 32u * (ay >> 3) + 1024u * (az >> 3);
+                if (slot >= c->n_slots) {
+                    c->h_models.resize((size_t)(slot + 1) * 512, 0u);
+                    c->n_slots = slot + 1;
+                }
+                c->h_models[(size_t)slot * 512 + (ax & 7u) + ((ay & 7u) << 3) + ((az & 7u) << 6)] = rgba[x + (size_t)w * (y + (size_t)h * z)];
+            }
+    c->atlas_dirty = true;
+    return UVT_OK;
+}
+
+// ---- camera -------------------------------------------------------------------------------------
+int uvt_set_camera(uvt_ctx *c, const uvt_camera *cam) { return uvt_set_cameras(c, cam, 1); }
+
+int uvt_set_cameras(uvt_ctx *c, const uvt_camera *cams, int n) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, cams && n >= 1, "need at least one camera");
+    c->cams.assign(cams, cams + n);
+    derive_cam(cams[0], c->cam0);
+    c->have_camera = true;
+    if ((uint32_t)n != c->layers) {
+        c->layers = (uint32_t)n;
+        if (c->W && c->H) {
+            UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+            int rc = alloc_gbuffer(c);
+            if (rc != UVT_OK) return rc;
+        }
+    }
+    if (n > 1) {
+        if (n > c->d_cams_capacity) {
+            UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_cams);
+            c->d_cams = nullptr;
+            UVT_CUDA(c, cudaMalloc(&c->d_cams, sizeof(CamDev) * n));
+            c->d_cams_capacity = n;
+        }
+        std::vector<CamDev> tmp(n);
+        for (int i = 0; i < n; ++i) derive_cam(cams[i], tmp[i]);
+        UVT_CUDA(c, cudaMemcpyAsync(c->d_cams, tmp.data(), sizeof(CamDev) * n, cudaMemcpyHostToDevice, c->stream));
+        UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return UVT_OK;
+}
+
+// ---- G-buffer -----------------------------------------------------------------------------------
+int uvt_resize(uvt_ctx *c, uint32_t width, uint32_t height) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, width >= 1 && height >= 1 && width <= 32768 && height <= 32768, "G-buffer size out of range");
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->W = width;
+    c->H = height;
+    return alloc_gbuffer(c);
+}
+
+int uvt_set_partition(uvt_ctx *c, uint32_t band_rows, uint32_t n_parts, uint32_t part) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, n_parts >= 1 && part < n_parts, "part must be < n_parts");
+    UVT_REQUIRE(c, band_rows >= kTileH && band_rows % kTileH == 0, "band_rows must be a positive multiple of 8");
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->band_rows = band_rows;
+    c->n_parts = n_parts;
+    c->part = part;
+    if (c->W && c->H) return alloc_gbuffer(c);
+    return UVT_OK;
+}
+
+int uvt_local_rows(uvt_ctx *c, uint32_t *rows) {
+    if (!c || !rows) return UVT_ERR_INVALID;
+    *rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
+    return UVT_OK;
+}
+
+// ---- passes -------------------------------------------------------------------------------------
+int uvt_dispatch_primary(uvt_ctx *c) {
+    if (!c) return UVT_ERR_INVALID;
+    int rc = pre_dispatch(c);
+    if (rc != UVT_OK) return rc;
+    PassTimer t(c, 0);
+    return launch_primary<false>(c);
+}
+
+int uvt_dispatch_secondary(uvt_ctx *c) {
+    if (!c) return UVT_ERR_INVALID;
+    int rc = pre_dispatch(c);
+    if (rc != UVT_OK) return rc;
+    PassTimer t(c, 1);
+    return launch_secondary<false>(c);
+}
+
+int uvt_shade(uvt_ctx *c) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, c->W && c->H, "no G-buffer (uvt_resize first)");
+    const uint32_t rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
+    const dim3 grid((c->W + 63) / 64, (rows + 3) / 4, c->layers);
+    PassTimer t(c, 2);
+    shade_kernel<<<grid, 256, 0, c->stream>>>(make_view(c, 0), make_gbuf(c), make_target(c));
+    return check_launch(c, "shade_kernel");
+}
+
+int uvt_dispatch_frame(uvt_ctx *c) {
+    if (!c) return UVT_ERR_INVALID;
+    int rc = pre_dispatch(c);
+    if (rc != UVT_OK) return rc;
+    const ViewDev v = make_view(c, c->params.primary_max_steps);
+    const GBufDev g = make_gbuf(c);
+    const dim3 grid = trace_grid(c);
+    const CamDev *cams = c->layers > 1 ? c->d_cams : nullptr;
+    PassTimer t(c, 3);
+    if (use_compact(c))
+        frame_kernel<WorldCompact, true><<<grid, kThreads, 0, c->stream>>>(world_compact(c), cams, c->cam0, v, c->params.shadow_max_steps, g, make_target(c));
+    else
+        frame_kernel<WorldRef, true><<<grid, kThreads, 0, c->stream>>>(world_ref(c), cams, c->cam0, v, c->params.shadow_max_steps, g, make_target(c));
+    return check_launch(c, "frame_kernel");
+}
+
+int uvt_pick(uvt_ctx *c, uvt_hit *out) {
+    if (!c || !out) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, c->have_camera, "no camera (uvt_set_camera first)");
+    int rc = ensure_ready(c);
+    if (rc != UVT_OK) return rc;
+    ViewDev v = make_view(c, c->params.edit_max_steps);
+    if (use_compact(c)) pick_kernel<WorldCompact><<<1, 128, 0, c->stream>>>(world_compact(c), c->cam0, v, c->d_pick);
+    else pick_kernel<WorldRef><<<1, 128, 0, c->stream>>>(world_ref(c), c->cam0, v, c->d_pick);
+    rc = check_launch(c, "pick_kernel");
+    if (rc != UVT_OK) return rc;
+    UVT_CUDA(c, cudaMemcpyAsync(out, c->d_pick, sizeof(uvt_hit), cudaMemcpyDeviceToHost, c->stream));
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return UVT_OK;
+}
+
+int uvt_sync(uvt_ctx *c) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return UVT_OK;
+}
+
+static int buffer_info(uvt_ctx *c, uvt_buffer_kind kind, void **ptr, size_t *bytes_per_px) {
+    switch (kind) {
+        case UVT_BUF_ALBEDO: *ptr = c->d_albedo; *bytes_per_px = 4; break;
+        case UVT_BUF_NORMAL: *ptr = c->d_normal; *bytes_per_px = 4; break;
+        case UVT_BUF_POSITION: *ptr = c->d_position; *bytes_per_px = 16; break;
+        case UVT_BUF_ILLUMINATION: *ptr = c->d_illum; *bytes_per_px = 4; break;
+        case UVT_BUF_FRAME: *ptr = c->d_frame; *bytes_per_px = 4; break;
+        case UVT_BUF_HIT: *ptr = c->d_hit; *bytes_per_px = sizeof(uvt_hit); break;
+        default: return set_error(c, UVT_ERR_INVALID, "unknown buffer kind %d", (int)kind);
+    }
+    if (!*ptr) return set_error(c, UVT_ERR_INVALID, "buffer %d is not allocated (uvt_resize / UVT_FLAG_HIT_BUFFER)", (int)kind);
+    return UVT_OK;
+}
+
+size_t uvt_buffer_bytes(uvt_ctx *c, uvt_buffer_kind kind) {
+    if (!c) return 0;
+    void *p;
+    size_t bpp;
+    if (buffer_info(c, kind, &p, &bpp) != UVT_OK) return 0;
+    return c->gbuf_pixels * bpp;
+}
+
+int uvt_readback(uvt_ctx *c, uvt_buffer_kind kind, void *dst, size_t bytes) {
+    if (!c || !dst) return UVT_ERR_INVALID;
+    void *p;
+    size_t bpp;
+    int rc = buffer_info(c, kind, &p, &bpp);
+    if (rc != UVT_OK) return rc;
+    UVT_REQUIRE(c, bytes <= c->gbuf_pixels * bpp, "readback larger than the buffer");
+    UVT_CUDA(c, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return UVT_OK;
+}
+
+int uvt_device_ptr(uvt_ctx *c, uvt_buffer_kind kind, void **dptr) {
+    if (!c || !dptr) return UVT_ERR_INVALID;
+    size_t bpp;
+    return buffer_info(c, kind, dptr, &bpp);
+}
+
+int uvt_bind_frame_target(uvt_ctx *c, void *dptr, uint32_t row_offset_rows, uint32_t global_rows) {
+    if (!c) return UVT_ERR_INVALID;
+    (void)row_offset_rows;
+    c->frame_target = (uint32_t *)dptr;
+    c->frame_target_global_rows = global_rows != 0;
+    return UVT_OK;
+}
+
+int uvt_alloc_pinned(uvt_ctx *c, size_t bytes, void **out) {
+    if (!c || !out) return UVT_ERR_INVALID;
+    UVT_CUDA(c, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return UVT_OK;
+}
+
+int uvt_free_pinned(uvt_ctx *c, void *p) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_CUDA(c, cudaFreeHost(p));
+    return UVT_OK;
+}
+
+int uvt_count_pass(uvt_ctx *c, int which, uvt_counters *out) {
+    if (!c || !out) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, which == 0 || which == 1, "which must be 0 (primary) or 1 (secondary)");
+    int rc = pre_dispatch(c);
+    if (rc != UVT_OK) return rc;
+    UVT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), c->stream));
+    rc = which == 0 ? launch_primary<true>(c) : launch_secondary<true>(c);
+    if (rc != UVT_OK) return rc;
+    DevCounters h;
+    UVT_CUDA(c, cudaMemcpyAsync(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    out->rays = h.rays; out->t_in = h.t_in; out->t_chunk = h.t_chunk; out->t_block = h.t_block;
+    out->hits = h.hits; out->early_out = h.early_out;
+    return UVT_OK;
+}
+
+int uvt_enable_timing(uvt_ctx *c, int on) {
+    if (!c) return UVT_ERR_INVALID;
+    c->timing = on != 0;
+    return UVT_OK;
+}
+
+int uvt_last_pass_ms(uvt_ctx *c, int which, float *ms) {
+    if (!c || !ms) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, which >= 0 && which < 4, "which must be 0..3");
+    UVT_REQUIRE(c, c->ev_valid[which], "pass has not run with timing enabled");
+    UVT_CUDA(c, cudaEventSynchronize(c->ev[which][1]));
+    UVT_CUDA(c, cudaEventElapsedTime(ms, c->ev[which][0], c->ev[which][1]));
+    return UVT_OK;
+}
+
+uint64_t uvt_launch_count(uvt_ctx *c) { return c ? c->launches : 0; }
+
+int uvt_deinterleave(uvt_ctx *c, const void *gathered, void *frame, uint32_t rows_per_part) {
+    if (!c || !gathered || !frame) return UVT_ERR_INVALID;
+    const dim3 grid((c->W + 255) / 256, c->H, 1);
+    deinterleave_kernel<<<grid, 256, 0, c->stream>>>((const uint32_t *)gathered, (uint32_t *)frame, c->W, c->H, c->band_rows, c->n_parts, rows_per_part);
+    return check_launch(c, "deinterleave_kernel");
+}
+
+int uvt_measure_l2_read_gbps(uvt_ctx *c, size_t bytes, int repeats, float *gbps) {
+    if (!c || !gbps) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, bytes >= 4096 && bytes % 16 == 0 && repeats >= 1, "bytes must be a multiple of 16, repeats >= 1");
+    uint4 *buf = nullptr;
+    UVT_CUDA(c, cudaMalloc(&buf, bytes));
+    UVT_CUDA(c, cudaMemsetAsync(buf, 1, bytes, c->stream));
+    const int blocks = c->sm_count * 8;
+    l2_read_kernel<<<blocks, 256, 0, c->stream>>>(buf, bytes / 16, 2, c->d_sink);  // warm: pull the buffer into L2
+    c->launches++;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, c->stream);
+    l2_read_kernel<<<blocks, 256, 0, c->stream>>>(buf, bytes / 16, repeats, c->d_sink);
+    cudaEventRecord(b, c->stream);
+    int rc = check_launch(c, "l2_read_kernel");
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf);
+    if (rc != UVT_OK) return rc;
+    *gbps = (float)((double)bytes * repeats / (ms * 1e-3) / 1e9);
+    return UVT_OK;
+}
+
+int uvt_measure_hbm_copy_gbps(uvt_ctx *c, size_t bytes, int repeats, float *gbps) {
+    if (!c || !gbps) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, bytes >= 4096 && bytes % 16 == 0 && repeats >= 1, "bytes must be a multiple of 16, repeats >= 1");
+    uint4 *src = nullptr, *dst = nullptr;
+    UVT_CUDA(c, cudaMalloc(&src, bytes));
+    UVT_CUDA(c, cudaMalloc(&dst, bytes));
+    UVT_CUDA(c, cudaMemsetAsync(src, 1, bytes, c->stream));
+    const int blocks = c->sm_count * 16;
+    copy_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, bytes / 16);
+    c->launches++;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, c->stream);
+    for (int r = 0; r < repeats; ++r) {
+        copy_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, bytes / 16);
+        c->launches++;
+    }
+    cudaEventRecord(b, c->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(src); cudaFree(dst);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "copy_kernel: %s", cudaGetErrorString(e));
+    *gbps = (float)(2.0 * (double)bytes * repeats / (ms * 1e-3) / 1e9);
+    return UVT_OK;
+}
+
+}  // extern "C"
