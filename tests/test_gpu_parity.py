@@ -1,0 +1,358 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): hit voxel coordinates, face ids, material (block word) and colour
+BIT-EXACT; G-buffer normal / position / illumination bit-exact; hit distance within 2 ulp; sky
+albedo and the shaded frame within 1/255 per channel.
+"""
+import numpy as np
+import pytest
+
+from conftest import camera_k0, camera_k1, pitch_yaw_matrix
+
+pytestmark = pytest.mark.gpu
+
+WATER = 0x1000000D
+
+
+def channel_diff(a, b):
+    a8 = a.view(np.uint8).astype(np.int16)
+    b8 = b.view(np.uint8).astype(np.int16)
+    return np.abs(a8 - b8)
+
+
+def ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    return np.abs(ai - bi)
+
+
+def assert_primary_parity(gpu, ref):
+    """gpu/ref: dicts with albedo, normal, position, hits."""
+    h, g = ref["hits"], gpu["hits"]
+    for f in ("px", "py", "pz", "block", "color", "face", "trips", "exit_kind"):
+        assert np.array_equal(g[f], h[f]), f"hit buffer field {f} differs at {np.argwhere(g[f] != h[f])[:5]}"
+    hit = h["face"] != 0
+    assert ulp_diff(g["distance"][hit], h["distance"][hit]).max(initial=0) <= 2
+    assert (g["distance"][~hit] == -1.0).all()
+    assert np.array_equal(gpu["normal"], ref["normal"])
+    assert np.array_equal(gpu["position"].view(np.uint32), ref["position"].view(np.uint32))
+    assert np.array_equal(gpu["albedo"][hit], ref["albedo"][hit])          # colours of hits: bit-exact
+    assert channel_diff(gpu["albedo"], ref["albedo"]).max() <= 1            # sky: 1/255
+
+
+def gpu_render(ctx, cam, three_pass=True):
+    ctx.set_camera(cam)
+    if three_pass:
+        ctx.dispatch_primary()
+        ctx.dispatch_secondary()
+        ctx.shade()
+    else:
+        ctx.dispatch_frame()
+    out = {k: ctx.readback(k) for k in ("albedo", "normal", "position", "illumination", "frame")}
+    try:
+        out["hits"] = ctx.readback("hit")
+    except Exception:
+        out["hits"] = None
+    return out
+
+
+@pytest.fixture(scope="module")
+def w1(uvt, scene_factory):
+    """W1 on the GPU: procgen(512) written into the ctx's pinned staging and committed through the C ABI."""
+    ctx = uvt.Context(0, hit_buffer=True)
+    sc = scene_factory(512, "procgen", ctx=ctx)
+    yield ctx, sc
+    ctx.close()
+
+
+@pytest.mark.parametrize("layout", ["compact", "reference"])
+@pytest.mark.parametrize("cam_name,size", [("k0", (320, 180)), ("k1", (320, 180)), ("k1", (1280, 720))])
+def test_frame_parity_w1(uvt, oracle, w1, layout, cam_name, size):
+    ctx, sc = w1
+    W, H = size
+    cam = camera_k0(oracle) if cam_name == "k0" else camera_k1(uvt, oracle)
+    ctx.set_layout(layout)
+    assert ctx.effective_layout() == layout
+    ctx.resize(W, H)
+    g = gpu_render(ctx, cam)
+    r = oracle.render(sc.oracle_world, cam, W, H)
+    assert_primary_parity(g, r)
+    assert np.array_equal(g["illumination"], r["illumination"])
+    assert channel_diff(g["frame"], r["frame"]).max() <= 1
+    assert (r["hits"]["face"] != 0).mean() > 0.3 and len(np.unique(r["illumination"])) == 3
+    # exact traversal counters (they define the algorithmic bytes of the roofline)
+    assert ctx.count_pass("primary") == {**r["primary_counters"]}
+    assert ctx.count_pass("secondary") == {**r["secondary_counters"]}
+
+
+def test_committed_golden_fixture(uvt, oracle, w1):
+    """The GPU against the committed oracle output (tests/golden/oracle_w1_*.npz)."""
+    import os
+    from conftest import GOLDEN
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    ctx.resize(96, 54)
+    for name, cam in (("k0_96x54", camera_k0(oracle)), ("k1_96x54", camera_k1(uvt, oracle))):
+        gold = np.load(os.path.join(GOLDEN, f"oracle_w1_{name}.npz"))
+        g = gpu_render(ctx, cam)
+        assert np.array_equal(g["hits"].view(np.uint8).reshape(-1), gold["hits"].view(np.uint8).reshape(-1)) or \
+            ulp_diff(g["hits"]["distance"], gold["hits"].view(g["hits"].dtype).reshape(54, 96)["distance"]).max() <= 2
+        for k in ("normal", "illumination"):
+            assert np.array_equal(g[k], gold[k])
+        assert np.array_equal(g["position"].view(np.uint32), gold["position"].view(np.uint32))
+        assert channel_diff(g["frame"], gold["frame"]).max() <= 1
+
+
+def test_fused_frame_equals_three_passes(uvt, oracle, w1):
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    ctx.resize(640, 360)
+    cam = camera_k1(uvt, oracle)
+    a = gpu_render(ctx, cam, three_pass=True)
+    b = gpu_render(ctx, cam, three_pass=False)
+    for k in ("albedo", "normal", "illumination", "frame"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["position"].view(np.uint32), b["position"].view(np.uint32))
+
+
+@pytest.mark.parametrize("size", [(1, 1), (17, 9), (33, 31), (250, 130)])
+def test_ragged_sizes(uvt, oracle, w1, size):
+    """Sizes that are not multiples of the 16x8 CTA tile (the reference over-dispatches and bounds-checks, primary.comp.glsl:28-29)."""
+    ctx, sc = w1
+    W, H = size
+    ctx.resize(W, H)
+    cam = camera_k1(uvt, oracle)
+    g = gpu_render(ctx, cam)
+    r = oracle.render(sc.oracle_world, cam, W, H)
+    assert_primary_parity(g, r)
+    assert np.array_equal(g["illumination"], r["illumination"])
+    assert channel_diff(g["frame"], r["frame"]).max() <= 1
+
+
+def test_random_poses_hit_buffers_bit_exact(uvt, oracle, w1):
+    """Random interior poses (the C5 pose distribution), hit buffers only."""
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    ctx.resize(160, 90)
+    rng = np.random.default_rng(5)
+    for i in range(12):
+        x, z = rng.uniform(20, 490, 2)
+        y = uvt.procgen.height(512, int(x), int(z)) + rng.uniform(3, 40)
+        cam = oracle.make_camera((x, y, z), pitch_yaw_matrix(uvt, rng.uniform(-0.6, 0.6), rng.uniform(0, 2 * np.pi)),
+                                 fov=rng.uniform(0.6, 2.2))
+        g = gpu_render(ctx, cam)
+        r = oracle.render(sc.oracle_world, cam, 160, 90)
+        assert_primary_parity(g, r)
+        assert np.array_equal(g["illumination"], r["illumination"])
+
+
+def test_camera_outside_and_degenerate_views(uvt, oracle, w1):
+    """Camera outside the map (AABB clip path), looking straight down/up (zero direction components)."""
+    ctx, sc = w1
+    ctx.resize(128, 72)
+    down = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, -1, 0, 0], [0, 0, 0, 1]], np.float32)
+    cams = [oracle.make_camera((-40.0, 60.0, 256.0), pitch_yaw_matrix(uvt, 0.3, np.pi / 2)),   # outside, looking in (+x)
+            oracle.make_camera((256.0, 700.0, 256.0), down),                                    # far above, looking down
+            oracle.make_camera((256.0, 30.0, 256.0), down),
+            oracle.make_camera((600.0, 30.0, 600.0), None),                                      # outside, looking away
+            oracle.make_camera((256.0, 25.0, 256.0), np.eye(4, dtype=np.float32), fov=0.314)]
+    for cam in cams:
+        g = gpu_render(ctx, cam)
+        r = oracle.render(sc.oracle_world, cam, 128, 72)
+        assert_primary_parity(g, r)
+        assert np.array_equal(g["illumination"], r["illumination"])
+
+
+def test_empty_world_and_single_block(uvt, oracle, scene_factory):
+    with uvt.Context(0, hit_buffer=True) as ctx:
+        sc = scene_factory(512, None, ctx=ctx)
+        ctx.resize(64, 36)
+        g = gpu_render(ctx, camera_k0(oracle))
+        r = oracle.render(sc.oracle_world, camera_k0(oracle), 64, 36)
+        assert_primary_parity(g, r)
+        assert (g["hits"]["face"] == 0).all() and (g["illumination"] == 0).all() and g["hits"]["trips"].max() == 192
+    with uvt.Context(0, hit_buffer=True) as ctx:
+        sc = scene_factory(512, lambda bm: bm.set(256, 0, 256, WATER), ctx=ctx)
+        ctx.resize(64, 64)
+        down = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, -1, 0, 0], [0, 0, 0, 1]], np.float32)
+        cam = oracle.make_camera((256.5, 4.0, 256.5), down)
+        g = gpu_render(ctx, cam)
+        rec = g["hits"][32, 32]
+        assert (rec["px"], rec["py"], rec["pz"], rec["face"], rec["trips"], rec["color"], rec["block"]) == (2052, 5, 2052, 4, 6, 0xFFFFCC99, WATER)
+        assert g["position"][32, 32].tolist() == [256.625, 0.75, 256.625, 1.0]
+        assert_primary_parity(g, oracle.render(sc.oracle_world, cam, 64, 64))
+
+
+def test_small_world_dims(uvt, oracle, scene_factory):
+    """MAP_DIMENSION other than 512 (the C3 world uses 2048): bounds and chunk-table strides follow dim."""
+    for dim in (64, 128):
+        with uvt.Context(0, hit_buffer=True, map_dim=dim) as ctx:
+            sc = scene_factory(dim, "procgen", ctx=ctx)
+            ctx.resize(96, 54)
+            cam = oracle.make_camera((dim / 2, 22.0, dim / 2), pitch_yaw_matrix(uvt, 0.4, 0.8))
+            g = gpu_render(ctx, cam)
+            r = oracle.render(sc.oracle_world, cam, 96, 54, oracle.params(dim))
+            assert_primary_parity(g, r)
+            assert np.array_equal(g["illumination"], r["illumination"])
+
+
+def test_unloaded_model_reads_empty_and_many_materials_fall_back(uvt, oracle, models, atlas, scene_factory):
+    """A block whose model slot was never uploaded reads as empty; > 255 distinct block words
+    cannot use the 8-bit compact bricks and must fall back to the reference layout, still bit-exact."""
+    def fill(bm):
+        for x in range(240, 272):
+            for z in range(240, 272):
+                bm.set(x, 0, z, WATER)
+                bm.set(x, 1, z, 0x10000000 | 200)          # model 200: not loaded
+        for i in range(300):
+            # 300 distinct block words (bits 15.. vary) that all resolve to loaded model slots (word & 32767 = i % 29)
+            bm.set(240 + i % 32, 3, 240 + i // 32, (i % 29) | 0x10000000 | ((i + 1) << 15))
+    with uvt.Context(0, hit_buffer=True) as ctx:
+        sc = scene_factory(512, fill, ctx=ctx)
+        assert ctx.effective_layout() == "reference"
+        ctx.resize(96, 54)
+        cam = oracle.make_camera((256.0, 12.0, 250.0), pitch_yaw_matrix(uvt, 0.9, 0.1))
+        g = gpu_render(ctx, cam)
+        r = oracle.render(sc.oracle_world, cam, 96, 54)
+        assert_primary_parity(g, r)
+        assert (r["hits"]["face"] != 0).any()
+
+
+def test_partition_union_equals_full_frame(uvt, oracle, w1):
+    """Multi-GPU image partition: interleaved row bands rendered separately reassemble to the full frame."""
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    W, H = 320, 200  # 25 bands of 8 rows: ragged against 4 parts
+    cam = camera_k1(uvt, oracle)
+    ctx.set_partition(8, 1, 0)
+    ctx.resize(W, H)
+    full = gpu_render(ctx, cam)
+    n_parts, band = 4, 16
+    frame = np.zeros((H, W), np.uint32)
+    pos = np.zeros((H, W, 4), np.float32)
+    for part in range(n_parts):
+        ctx.set_partition(band, n_parts, part)
+        g = gpu_render(ctx, cam)
+        rows = ctx.local_rows()
+        assert g["frame"].shape == (rows, W)
+        for ly in range(rows):
+            lb = ly // band
+            y = (lb * n_parts + part) * band + ly % band
+            if y < H:
+                frame[y] = g["frame"][ly]
+                pos[y] = g["position"][ly]
+    ctx.set_partition(8, 1, 0)
+    assert np.array_equal(frame, full["frame"])
+    assert np.array_equal(pos.view(np.uint32), full["position"].view(np.uint32))
+
+
+def test_batched_poses_equal_single_dispatches(uvt, oracle, w1):
+    ctx, sc = w1
+    ctx.resize(160, 90)
+    cams = np.stack([camera_k0(oracle), camera_k1(uvt, oracle), oracle.make_camera((100.0, 40.0, 300.0), pitch_yaw_matrix(uvt, 0.2, 2.0))])
+    singles = [gpu_render(ctx, c) for c in cams]
+    ctx.set_camera(cams)
+    ctx.dispatch_primary(); ctx.dispatch_secondary(); ctx.shade()
+    fr, hb = ctx.readback("frame"), ctx.readback("hit")
+    assert fr.shape == (3, 90, 160)
+    for i in range(3):
+        assert np.array_equal(fr[i], singles[i]["frame"])
+        assert np.array_equal(hb[i].view(np.uint8), singles[i]["hits"].view(np.uint8))
+    ctx.set_camera(cams[0])
+
+
+def test_pick_ray_matches_oracle(uvt, oracle, w1):
+    """terrain_edit.comp.glsl: the centre ray with a 64-trip cap."""
+    ctx, sc = w1
+    cam = camera_k1(uvt, oracle)
+    ctx.set_camera(cam)
+    rec = ctx.pick()
+    # centre ray = uv 0: same as pixel (W/2, H/2) of any even-sized frame
+    o, d, s = oracle.primary_ray(cam, 2, 2, 1, 1, 512)
+    h = oracle.trace_map(sc.oracle_world, s, d, 64)
+    assert (int(rec["px"]), int(rec["py"]), int(rec["pz"])) == h["p"]
+    assert (int(rec["face"]), int(rec["block"]), int(rec["color"]), int(rec["trips"])) == (h["face"], h["block"], h["data"], h["trips"])
+
+
+def test_game_mirror_call_order(uvt, oracle, models, w1):
+    """src/game.zig:54-129,224-256 replayed through the gfx mirror: same result as the direct C calls."""
+    with uvt.Context(0) as ctx:
+        game = uvt.game.Game(ctx, dim=512, width=320, height=180, models=models)
+        game.update()
+        game.pre_render()
+        game.render()
+        frame = ctx.readback("frame")
+        _, sc = w1
+        r = oracle.render(sc.oracle_world, camera_k0(oracle), 320, 180)
+        assert channel_diff(frame, r["frame"]).max() <= 1
+        assert np.array_equal(ctx.readback("illumination"), r["illumination"])
+        with pytest.raises(uvt.UvtError):
+            game.primary_trace_pipeline.dispatch(1, 1, 1)  # does not cover the G-buffer
+        game.window_resized(100, 60)
+        game.render()
+        assert ctx.readback("frame").shape == (60, 100)
+        game.deinit()
+
+
+def test_errors_are_reported_not_fatal(uvt, oracle):
+    with uvt.Context(0) as ctx:
+        with pytest.raises(uvt.UvtError):
+            ctx.dispatch_primary()           # no G-buffer
+        ctx.resize(32, 32)
+        with pytest.raises(uvt.UvtError):
+            ctx.dispatch_primary()           # no camera
+        ctx.set_camera(camera_k0(oracle))
+        with pytest.raises(uvt.UvtError) as e:
+            ctx.dispatch_primary()           # no world
+        assert "world" in e.value.message
+        with pytest.raises(uvt.UvtError):
+            ctx.readback("hit")              # hit buffer not enabled
+        with pytest.raises(uvt.UvtError):
+            ctx.set_partition(5, 2, 0)       # band not a multiple of 8
+
+
+def test_world_edit_then_recommit(uvt, oracle, scene_factory):
+    """VoxelBrickmap.set after init is visible after the next bind() (the reference mapping is live)."""
+    with uvt.Context(0, hit_buffer=True) as ctx:
+        sc = scene_factory(512, "procgen", ctx=ctx)
+        ctx.resize(160, 90)
+        cam = camera_k0(oracle)
+        before = gpu_render(ctx, cam)
+        for y in range(20, 40):
+            for x in range(250, 262):
+                sc.bm.set(x, y, 270, uvt.voxel.Voxel(11, True))   # a rock wall in front of the camera, allocates new bricks
+        sc.bm.bind(9)
+        after = gpu_render(ctx, cam)
+        world = oracle.World(512, sc.bm.chunks().copy(), sc.bm.bricks().copy(), sc.oracle_world.atlas)
+        r = oracle.render(world, cam, 160, 90)
+        assert_primary_parity(after, r)
+        assert not np.array_equal(before["hits"]["block"], after["hits"]["block"])
+
+
+# ---- full-size, size-independent properties (BASELINE configs) -------------------------------------
+@pytest.mark.parametrize("size", [(1920, 1080), (3840, 2160)])
+def test_full_size_layouts_agree_and_rows_match_oracle(uvt, oracle, w1, size):
+    ctx, sc = w1
+    W, H = size
+    cam = camera_k1(uvt, oracle)
+    ctx.resize(W, H)
+    ctx.set_layout("compact")
+    a = gpu_render(ctx, cam)
+    ca = ctx.count_pass("primary")
+    ctx.set_layout("reference")
+    b = gpu_render(ctx, cam)
+    cb = ctx.count_pass("primary")
+    ctx.set_layout("compact")
+    assert np.array_equal(a["hits"].view(np.uint8), b["hits"].view(np.uint8))
+    for k in ("albedo", "normal", "illumination", "frame"):
+        assert np.array_equal(a[k], b[k]), k
+    assert ca == cb and ca["rays"] == W * H
+    assert ca["t_in"] == int(a["hits"]["trips"].astype(np.int64).sum())
+    # a band of rows against the oracle at full resolution: the oracle is asked for the whole frame
+    # only at 1080p (about a second); at 4K it checks the identity of hit statistics instead
+    if (W, H) == (1920, 1080):
+        r = oracle.render(sc.oracle_world, cam, W, H)
+        assert_primary_parity(a, r)
+        assert np.array_equal(a["illumination"], r["illumination"])
+        assert channel_diff(a["frame"], r["frame"]).max() <= 1
+        assert ca == r["primary_counters"]
