@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) primary_kernel(WorldArgs<World> wa, 
         float dx, dy, dz, sx, sy, sz;
         primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
         Hit h;
-        trace_map<World, COUNT>(w, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+        trace<World, COUNT>(w, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
         const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
         float dist = -1.0f;
         if (h.data != 0) {  // primary.comp.glsl:58-62
@@ -248,7 +248,7 @@ __device__ __forceinline__ uint32_t shadow_pixel(const World &w, const ViewDev &
                 nz = (float)((normal >> 16) & 255u) / 255.0f;
     const float ox = posx + nx * 0.001f, oy = posy + ny * 0.001f, oz = posz + nz * 0.001f;
     Hit h;
-    trace_map<World, COUNT>(w, ox, oy, oz, UVT_SUN_X, UVT_SUN_Y, UVT_SUN_Z, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+    trace<World, COUNT>(w, ox, oy, oz, UVT_SUN_X, UVT_SUN_Y, UVT_SUN_Z, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
     hit = h.data != 0;
     bool shadowed = h.data != 0;
     if (v.entities && !shadowed) {  // an entity hit only matters when the terrain ray missed (same -0.3 either way)
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kThreads) frame_kernel(WorldArgs<World> wa, co
     primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
     Hit h;
     TripCounts tc;
-    trace_map<World, false>(w, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+    trace<World, false>(w, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
     const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
     uint32_t albedo, normal, illum = 0u;
     float4 pos;
@@ -413,7 +413,7 @@ __global__ void pick_kernel(WorldArgs<World> wa, CamDev cam, ViewDev v, uint8_t 
     const float t0 = gmax(tn, 0.0f);
     Hit h;
     TripCounts tc;
-    trace_map<World, false>(w, cam.pos[0] + dx * t0 - v.epsilon, cam.pos[1] + dy * t0 - v.epsilon, cam.pos[2] + dz * t0 - v.epsilon,
+    trace<World, false>(w, cam.pos[0] + dx * t0 - v.epsilon, cam.pos[1] + dy * t0 - v.epsilon, cam.pos[2] + dz * t0 - v.epsilon,
                             dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
     float dist = -1.0f;
     if (h.data != 0) {
@@ -444,6 +444,66 @@ __global__ void repack_bricks_kernel(const uint32_t *__restrict__ bricks, uint8_
         }
         *reinterpret_cast<uint32_t *>(bricks8 + i) = packed;
     }
+}
+
+
+// ---- chunk distance field for the fast path (trace_map_fast) ------------------------------
+// dist[c] = Chebyshev distance (in chunks) from chunk c to the nearest NON-EMPTY chunk or to the
+// outside of the map, capped at kFieldCap; separable min-max passes over x, y, z.
+constexpr int kFieldCap = 32;
+
+__global__ void field_pass_x_kernel(const uint32_t *__restrict__ chunks, uint8_t *__restrict__ out, int cd) {
+    const size_t n = (size_t)cd * cd * cd;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % cd);
+    int best = kFieldCap;
+    if (chunks[i] != 0) best = 0;
+    else {
+        for (int k = 1; k < best; ++k) {
+            const bool lo = (x - k < 0) || chunks[i - k] != 0;
+            const bool hi = (x + k >= cd) || chunks[i + k] != 0;
+            if (lo || hi) { best = k; break; }
+        }
+    }
+    out[i] = (uint8_t)best;
+}
+
+// axis stride `stride`, coordinate along the axis = (i / stride) % cd
+__global__ void field_pass_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int cd, size_t stride) {
+    const size_t n = (size_t)cd * cd * cd;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = (int)((i / stride) % cd);
+    int best = in[i];
+    for (int k = 1; k < best; ++k) {
+        const int lo = (a - k < 0) ? 0 : (int)in[i - (size_t)k * stride];
+        const int hi = (a + k >= cd) ? 0 : (int)in[i + (size_t)k * stride];
+        const int v = max(k, min(lo, hi));
+        best = min(best, v);
+    }
+    out[i] = (uint8_t)best;
+}
+
+// chunks2[(cd+1)^3]: bit 31 = empty chunk, low byte = n_free = max(8*(dist-1) - 2, 0); else 0-based brick index
+__global__ void build_chunks2_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ dist, uint32_t *__restrict__ chunks2, int cd) {
+    const int cd1 = cd + 1;
+    const size_t n = (size_t)cd1 * cd1 * cd1;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % cd1), y = (int)((i / cd1) % cd1), z = (int)(i / ((size_t)cd1 * cd1));
+    uint32_t e = 0x80000000u;  // guard layer: empty, nothing known about what follows
+    if (x < cd && y < cd && z < cd) {
+        const size_t j = (size_t)x + (size_t)cd * ((size_t)y + (size_t)z * cd);
+        const uint32_t c = chunks[j];
+        if (c != 0) e = c - 1u;
+        else {
+            const int r = (int)dist[j] - 1;  // rings of empty in-map chunks around this one
+            const int nf = 8 * r - 2;
+            e = 0x80000000u | (uint32_t)min(max(nf, 0), 255);
+        }
+    }
+    chunks2[i] = e;
 }
 
 // ---- bandwidth probes (roofline denominators) ----------------------------------

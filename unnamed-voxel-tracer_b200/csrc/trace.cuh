@@ -8,6 +8,7 @@
 #pragma once
 
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace uvt {
@@ -69,12 +70,14 @@ struct WorldRef {
 // (512 B instead of 2 KiB), per-material 512-bit sub-voxel occupancy masks staged in shared
 // memory, colours and block words resolved only at the hit.
 struct WorldCompact {
-    const uint32_t *__restrict__ chunks;
+    const uint32_t *__restrict__ chunks;    // reference encoding (0 = empty else brick+1); generic path only
+    const uint32_t *__restrict__ chunks2;   // [(cd+1)^3] fast-path encoding, see trace_map_fast
     const uint8_t *__restrict__ bricks8;    // [n_bricks][512], value = material id (0 = empty)
     const uint32_t *__restrict__ mat_word;  // [256] material id -> block word
     const uint32_t *__restrict__ mat_color; // [256][512] material id -> model texels
     const uint32_t *smem_masks;             // [256][16] shared-memory copy of the occupancy masks
     uint32_t cd;
+    uint32_t cd1;                           // cd + 1: stride of chunks2 (one guard layer on the high side)
 
     __device__ __forceinline__ uint32_t block_at(uint32_t px, uint32_t py, uint32_t pz, bool &chunk_hit) const {
         const uint32_t bx = px >> 3, by = py >> 3, bz = pz >> 3;
@@ -190,6 +193,153 @@ __device__ __forceinline__ void trace_map(const World &w, float ox, float oy, fl
         else { gz += posz ? istep : -istep; wz = posz ? 0.0f : reset; }
     }
     out.trips = (uint32_t)trip;
+}
+
+// ---- traceMap, B200 fast path ----------------------------------------------------------
+// Same trips, same arithmetic as trace_map (map.glsl:83-168); what changes is what is FETCHED:
+//
+//  * chunks2[(cd+1)^3] marks empty chunks with bit 31 and carries in its low byte n_free, the
+//    number of FOLLOWING trips that are guaranteed to (a) stay inside the map and (b) look up
+//    an empty block, derived from the Chebyshev distance (in chunks) to the nearest non-empty
+//    chunk or map face (build_chunk_field_*).  Such trips run the DDA arithmetic only — no
+//    bounds test, no `pos`, no loads.  Proof of the bound: at 8-sub-voxel steps g moves exactly
+//    one block along one axis per trip, `pos` is within one block of g (within in [-1, 8+ulp]),
+//    so after j trips the looked-up block is within j+2 blocks of the block looked up now; with
+//    R empty in-map chunk rings around this chunk every block within 8R is empty, hence
+//    n_free = 8R - 2.
+//  * the guard layer of chunks2 (index cd on any axis) removes the chunk-range test: `pos` can
+//    exceed the map by at most one block on the high side while g is in bounds.
+//  * bricks hold one byte per block; sub-voxel occupancy is a bit test in shared memory; colour
+//    and block word are fetched once, at the hit.
+//  * per-phase constants (target face, reset value, signed step per axis) are kept in registers
+//    and rewritten only when the step size changes.
+//
+// Rays with non-finite reciprocals or origins beyond 2^20 sub-voxels take the generic path,
+// whose corner-case behaviour (NaN ordering, saturation) is the specification.
+template <bool COUNT>
+__device__ __forceinline__ void trace_map_fast(const WorldCompact &w, float ox, float oy, float oz, float dx, float dy, float dz,
+                                               int max_steps, int bound, Hit &out, TripCounts &tc) {
+    if (dx == 0.0f) dx = 0.001f;
+    if (dy == 0.0f) dy = 0.001f;
+    if (dz == 0.0f) dz = 0.001f;
+    const float invx = 1.0f / dx, invy = 1.0f / dy, invz = 1.0f / dz;
+    const float o8x = ox * 8.0f, o8y = oy * 8.0f, o8z = oz * 8.0f;
+    const bool sane = fabsf(invx) < 1e30f && fabsf(invy) < 1e30f && fabsf(invz) < 1e30f &&
+                      fabsf(dx) < 1e30f && fabsf(dy) < 1e30f && fabsf(dz) < 1e30f &&
+                      fabsf(o8x) < 1048576.0f && fabsf(o8y) < 1048576.0f && fabsf(o8z) < 1048576.0f;
+    if (!sane) {
+        trace_map<WorldCompact, COUNT>(w, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
+        return;
+    }
+    const bool posx = dx > 0.0f, posy = dy > 0.0f, posz = dz > 0.0f;
+
+    int gx = __float2int_rz(o8x), gy = __float2int_rz(o8y), gz = __float2int_rz(o8z);
+    float wx = o8x - (float)gx, wy = o8y - (float)gy, wz = o8z - (float)gz;
+
+    // phase constants, stepSize 0
+    float tgx = posx ? 1.0f : 0.0f, tgy = posy ? 1.0f : 0.0f, tgz = posz ? 1.0f : 0.0f;          // float(rayPositivity << step)
+    float rsx = posx ? 0.0f : 0.999f, rsy = posy ? 0.0f : 0.999f, rsz = posz ? 0.0f : 0.999f;    // float((1 - pos) << step) * 0.999f
+    int isx = posx ? 1 : -1, isy = posy ? 1 : -1, isz = posz ? 1 : -1;                           // raySign << step
+    bool big = false;
+    bool mx = true, my = false;  // minIdx == 0 / == 1 of the previous trip (initially 0)
+    int free_trips = 0;
+
+    out.data = 0;
+    out.hx = out.hy = out.hz = -1.0f;
+    out.px = out.py = out.pz = 0xFFFFFFFFu;
+    out.block = 0;
+    out.face = 0;
+    out.exit_kind = 1;
+    if (COUNT) tc.t_in = tc.t_chunk = tc.t_block = 0;
+
+    const uint32_t cd1 = w.cd1;
+    int trip = 0;
+    for (; trip < max_steps; ++trip) {
+        if (free_trips > 0) {
+            --free_trips;
+            if (COUNT) tc.t_in++;
+        } else {
+            if ((unsigned)gx >= (unsigned)bound || (unsigned)gy >= (unsigned)bound || (unsigned)gz >= (unsigned)bound) {
+                out.exit_kind = 2;
+                break;
+            }
+            if (COUNT) tc.t_in++;
+            const uint32_t px = (uint32_t)gx + __float2uint_rz(wx);
+            const uint32_t py = (uint32_t)gy + __float2uint_rz(wy);
+            const uint32_t pz = (uint32_t)gz + __float2uint_rz(wz);
+            const uint32_t e = __ldg(&w.chunks2[(px >> 6) + cd1 * ((py >> 6) + (pz >> 6) * cd1)]);
+            uint32_t mat = 0;
+            if ((int)e < 0) {
+                free_trips = (int)(e & 0xFFu);
+            } else {
+                if (COUNT) tc.t_chunk++;
+                mat = __ldg(&w.bricks8[(size_t)e * 512u + (((px >> 3) & 7u) | (py & 0x38u) | ((pz & 0x38u) << 3))]);
+            }
+            if (mat != 0) {
+                if (COUNT) tc.t_block++;
+                const uint32_t bit = (px & 7u) | ((py & 7u) << 3) | ((pz & 7u) << 6);
+                const uint32_t word = w.smem_masks[mat * 16u + (bit >> 5)];
+                if ((word >> (bit & 31u)) & 1u) {
+                    out.data = __ldg(&w.mat_color[mat * 512u + bit]);
+                    out.face = mx ? (posx ? 1u : 2u) : (my ? (posy ? 3u : 4u) : (posz ? 5u : 6u));
+                    out.hx = (float)gx + wx;
+                    out.hy = (float)gy + wy;
+                    out.hz = (float)gz + wz;
+                    out.px = px; out.py = py; out.pz = pz;
+                    out.block = __ldg(&w.mat_word[mat]);
+                    out.exit_kind = 0;
+                    out.trips = (uint32_t)trip + 1u;
+                    return;
+                }
+                if (big) {  // drop to sub-voxel steps (map.glsl:131-135)
+                    gx += __float2int_rz(wx);
+                    gy += __float2int_rz(wy);
+                    gz += __float2int_rz(wz);
+                    wx = wx - floorf(wx);
+                    wy = wy - floorf(wy);
+                    wz = wz - floorf(wz);
+                    big = false;
+                    tgx = posx ? 1.0f : 0.0f; tgy = posy ? 1.0f : 0.0f; tgz = posz ? 1.0f : 0.0f;
+                    rsx = posx ? 0.0f : 0.999f; rsy = posy ? 0.0f : 0.999f; rsz = posz ? 0.0f : 0.999f;
+                    isx = posx ? 1 : -1; isy = posy ? 1 : -1; isz = posz ? 1 : -1;
+                }
+            } else if (!big) {  // rise to block steps (map.glsl:140-144)
+                wx += (float)(gx & 7);
+                wy += (float)(gy & 7);
+                wz += (float)(gz & 7);
+                gx &= ~7;
+                gy &= ~7;
+                gz &= ~7;
+                big = true;
+                tgx = posx ? 8.0f : 0.0f; tgy = posy ? 8.0f : 0.0f; tgz = posz ? 8.0f : 0.0f;
+                rsx = posx ? 0.0f : 8.0f * 0.999f; rsy = posy ? 0.0f : 8.0f * 0.999f; rsz = posz ? 0.0f : 8.0f * 0.999f;
+                isx = posx ? 8 : -8; isy = posy ? 8 : -8; isz = posz ? 8 : -8;
+            }
+        }
+
+        // dda stepping (map.glsl:157-162)
+        const float tx = (tgx - wx) * invx;
+        const float ty = (tgy - wy) * invy;
+        const float tz = (tgz - wz) * invz;
+        mx = (tx < ty) && (tx < tz);
+        my = !(tx < ty) && (ty < tz);
+        const float tm = mx ? tx : (my ? ty : tz);
+        wx += dx * tm;
+        wy += dy * tm;
+        wz += dz * tm;
+        if (mx) { gx += isx; wx = rsx; }
+        else if (my) { gy += isy; wy = rsy; }
+        else { gz += isz; wz = rsz; }
+    }
+    out.trips = (uint32_t)trip;
+}
+
+// dispatch: the compact world takes the fast path
+template <class World, bool COUNT>
+__device__ __forceinline__ void trace(const World &w, float ox, float oy, float oz, float dx, float dy, float dz,
+                                      int max_steps, int bound, Hit &out, TripCounts &tc) {
+    if constexpr (std::is_same<World, WorldCompact>::value) trace_map_fast<COUNT>(w, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
+    else trace_map<World, COUNT>(w, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
 }
 
 }  // namespace uvt

@@ -46,6 +46,7 @@ struct uvt_ctx {
     size_t d_brick_capacity = 0;
     uint8_t *d_bricks8 = nullptr;
     size_t d_brick8_capacity = 0;
+    uint32_t *d_chunks2 = nullptr;  // fast-path chunk table [(cd+1)^3]
     bool world_committed = false;
 
     // ---- atlas: host copy by slot (slot = x/8 + 32*(y/8) + 1024*(z/8)), device [n_slots][512]
@@ -233,6 +234,8 @@ WorldArgs<WorldRef> world_ref(const uvt_ctx *c) {
 WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     WorldArgs<WorldCompact> a;
     a.w.chunks = c->d_chunks;
+    a.w.chunks2 = c->d_chunks2;
+    a.w.cd1 = c->cd + 1;
     a.w.bricks8 = c->d_bricks8;
     a.w.mat_word = c->d_mat_word;
     a.w.mat_color = c->d_mat_color;
@@ -396,7 +399,7 @@ void uvt_destroy(uvt_ctx *c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     free_gbuffer(c);
     cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
-    cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models);
+    cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
     cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink);
     for (int i = 0; i < 4; ++i)
@@ -428,7 +431,10 @@ int uvt_set_layout(uvt_ctx *c, uint32_t layout) {
     return UVT_OK;
 }
 
-int uvt_effective_layout(uvt_ctx *c) { return c ? (use_compact(c) ? UVT_LAYOUT_COMPACT : UVT_LAYOUT_REFERENCE) : UVT_ERR_INVALID; }
+int uvt_effective_layout(uvt_ctx *c) {
+    if (!c) return UVT_ERR_INVALID;
+    return use_compact(c) ? (int)UVT_LAYOUT_COMPACT : (int)UVT_LAYOUT_REFERENCE;
+}
 
 int uvt_set_max_steps(uvt_ctx *c, uint32_t primary, uint32_t shadow) {
     if (!c) return UVT_ERR_INVALID;
@@ -481,9 +487,10 @@ int uvt_world_alloc(uvt_ctx *c, uint32_t dim, uint32_t **chunks_host, uint32_t *
     UVT_REQUIRE(c, brick_capacity > 0, "brick_capacity must be > 0");
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
-    cudaFree(c->d_chunks);
+    cudaFree(c->d_chunks); cudaFree(c->d_chunks2);
     c->h_chunks = c->h_bricks = nullptr;
     c->d_chunks = nullptr;
+    c->d_chunks2 = nullptr;
     c->dim = dim;
     c->cd = dim / 8;
     c->params.map_dim = dim;
@@ -493,6 +500,7 @@ int uvt_world_alloc(uvt_ctx *c, uint32_t dim, uint32_t **chunks_host, uint32_t *
     std::memset(c->h_chunks, 0, n_chunks * 4);              // voxel.zig:34
     std::memset(c->h_bricks, 0, brick_capacity * 2048);     // GL zero-initialised storage
     UVT_CUDA(c, cudaMalloc(&c->d_chunks, n_chunks * 4));
+    UVT_CUDA(c, cudaMalloc(&c->d_chunks2, (size_t)(c->cd + 1) * (c->cd + 1) * (c->cd + 1) * 4));
     c->h_capacity = brick_capacity;
     c->n_bricks = 0;
     c->world_committed = false;
@@ -589,6 +597,25 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
             cudaFree(d_vals);
             if (rc != UVT_OK) return rc;
         }
+    }
+    if (c->compact_ok) {
+        // chunk distance field -> fast-path chunk table
+        const int cd = (int)c->cd;
+        uint8_t *f0 = nullptr, *f1 = nullptr;
+        UVT_CUDA(c, cudaMalloc(&f0, n_chunks));
+        UVT_CUDA(c, cudaMalloc(&f1, n_chunks));
+        const unsigned blocks = (unsigned)((n_chunks + 255) / 256);
+        field_pass_x_kernel<<<blocks, 256, 0, c->stream>>>(c->d_chunks, f0, cd);
+        field_pass_kernel<<<blocks, 256, 0, c->stream>>>(f0, f1, cd, (size_t)cd);
+        field_pass_kernel<<<blocks, 256, 0, c->stream>>>(f1, f0, cd, (size_t)cd * cd);
+        const size_t n2 = (size_t)(cd + 1) * (cd + 1) * (cd + 1);
+        build_chunks2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(c->d_chunks, f0, c->d_chunks2, cd);
+        int rc = check_launch(c, "chunk field kernels");
+        c->launches += 3;
+        cudaStreamSynchronize(c->stream);
+        cudaFree(f0);
+        cudaFree(f1);
+        if (rc != UVT_OK) return rc;
     }
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->n_bricks = n_bricks;
@@ -758,16 +785,16 @@ static int buffer_info(uvt_ctx *c, uvt_buffer_kind kind, void **ptr, size_t *byt
 
 size_t uvt_buffer_bytes(uvt_ctx *c, uvt_buffer_kind kind) {
     if (!c) return 0;
-    void *p;
-    size_t bpp;
+    void *p = nullptr;
+    size_t bpp = 0;
     if (buffer_info(c, kind, &p, &bpp) != UVT_OK) return 0;
     return c->gbuf_pixels * bpp;
 }
 
 int uvt_readback(uvt_ctx *c, uvt_buffer_kind kind, void *dst, size_t bytes) {
     if (!c || !dst) return UVT_ERR_INVALID;
-    void *p;
-    size_t bpp;
+    void *p = nullptr;
+    size_t bpp = 0;
     int rc = buffer_info(c, kind, &p, &bpp);
     if (rc != UVT_OK) return rc;
     UVT_REQUIRE(c, bytes <= c->gbuf_pixels * bpp, "readback larger than the buffer");
