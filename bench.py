@@ -263,6 +263,7 @@ def run_ours(args):
     alg_primary = 4 * (cp["t_in"] + cp["t_chunk"] + cp["t_block"]) + 24 * cp["rays"]
     rays_step = cp["rays"]
     alg_step = alg_primary
+    fetch = ctx.fetch_stats("primary") if ctx.effective_layout() == "compact" else None
     if shadows:
         ctx.dispatch_primary()
         cs = ctx.count_pass("secondary")
@@ -351,6 +352,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel_ms": kms,
                          "algorithmic_bytes_per_launch": alg_step,
+                         "primary_trips": cp["t_in"], "primary_trips_with_fetch": fetch["lookups"] if fetch else cp["t_in"],
                          "note": "algorithmic bytes = reference access pattern (4*T_in+4*T_chunk+4*T_block+G-buffer), exact counters; "
                                  "the traversal data is cache resident, so the binding roofline is L2 (roofline_l2)"},
             "roofline_l2": {"bound": "l2", "achieved": achieved, "peak": l2_gbps, "unit": "GB/s", "frac": achieved / l2_gbps,

@@ -190,7 +190,7 @@ struct WorldArgs<WorldCompact> {
 };
 
 // ---- primary pass ------------------------------------------------------------------------
-template <class World, bool COUNT, bool HITBUF>
+template <class World, int COUNT, bool HITBUF>
 __global__ void __launch_bounds__(kThreads) primary_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0,
                                                            ViewDev v, GBufDev gb, DevCounters *counters) {
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
@@ -206,11 +206,11 @@ __global__ void __launch_bounds__(kThreads) primary_kernel(WorldArgs<World> wa, 
 
     TripCounts tc = {0, 0, 0};
     uint32_t is_hit = 0;
+    float dx = 0.0f, dy = 0.0f, dz = 1.0f, sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    if (valid) primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
+    Hit h;
+    trace<World, COUNT>(w, valid, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);  // all 32 lanes
     if (valid) {
-        float dx, dy, dz, sx, sy, sz;
-        primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
-        Hit h;
-        trace<World, COUNT>(w, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
         const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
         float dist = -1.0f;
         if (h.data != 0) {  // primary.comp.glsl:58-62
@@ -241,14 +241,15 @@ __global__ void __launch_bounds__(kThreads) primary_kernel(WorldArgs<World> wa, 
 }
 
 // shadow ray of one pixel: secondary.comp.glsl:36-50.  Returns the illumination texel.
-template <class World, bool COUNT>
-__device__ __forceinline__ uint32_t shadow_pixel(const World &w, const ViewDev &v, float posx, float posy, float posz,
+template <class World, int COUNT>
+__device__ __forceinline__ uint32_t shadow_pixel(const World &w, bool active, const ViewDev &v, float posx, float posy, float posz,
                                                  uint32_t normal, TripCounts &tc, uint32_t &hit) {
     const float nx = (float)(normal & 255u) / 255.0f, ny = (float)((normal >> 8) & 255u) / 255.0f,
                 nz = (float)((normal >> 16) & 255u) / 255.0f;
     const float ox = posx + nx * 0.001f, oy = posy + ny * 0.001f, oz = posz + nz * 0.001f;
     Hit h;
-    trace<World, COUNT>(w, ox, oy, oz, UVT_SUN_X, UVT_SUN_Y, UVT_SUN_Z, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+    trace<World, COUNT>(w, active, ox, oy, oz, UVT_SUN_X, UVT_SUN_Y, UVT_SUN_Z, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);  // all 32 lanes
+    if (!active) { hit = 0; return 0u; }
     hit = h.data != 0;
     bool shadowed = h.data != 0;
     if (v.entities && !shadowed) {  // an entity hit only matters when the terrain ray missed (same -0.3 either way)
@@ -260,7 +261,7 @@ __device__ __forceinline__ uint32_t shadow_pixel(const World &w, const ViewDev &
 }
 
 // ---- secondary pass ------------------------------------------------------------------------
-template <class World, bool COUNT>
+template <class World, int COUNT>
 __global__ void __launch_bounds__(kThreads) secondary_kernel(WorldArgs<World> wa, ViewDev v, GBufDev gb, DevCounters *counters) {
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
     World w = wa.w;
@@ -273,16 +274,19 @@ __global__ void __launch_bounds__(kThreads) secondary_kernel(WorldArgs<World> wa
     const bool valid = v.global_row(ly, y) && x < v.W;
     TripCounts tc = {0, 0, 0};
     uint32_t traced = 0, early = 0, hit = 0;
+    const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
+    float4 pos = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+    uint32_t nrm = 0;
     if (valid) {
-        const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
-        const float4 pos = gb.position[i];
-        if (pos.x < 0.0f || pos.y < 0.0f || pos.z < 0.0f) {  // :26-29
-            gb.illum[i] = 0u;
-            early = 1;
-        } else {
-            traced = 1;
-            gb.illum[i] = shadow_pixel<World, COUNT>(w, v, pos.x, pos.y, pos.z, gb.normal[i], tc, hit);
-        }
+        pos = gb.position[i];
+        nrm = gb.normal[i];
+    }
+    const bool shoot = valid && !(pos.x < 0.0f || pos.y < 0.0f || pos.z < 0.0f);  // :26-29
+    const uint32_t il = shadow_pixel<World, COUNT>(w, shoot, v, pos.x, pos.y, pos.z, nrm, tc, hit);  // all 32 lanes
+    if (valid) {
+        gb.illum[i] = shoot ? il : 0u;
+        traced = shoot ? 1u : 0u;
+        early = shoot ? 0u : 1u;
     }
     if (COUNT) {
         warp_add(&counters->rays, traced);
@@ -349,13 +353,13 @@ __global__ void __launch_bounds__(kThreads) frame_kernel(WorldArgs<World> wa, co
     }
     uint32_t x, ly, y;
     tile_pixel(x, ly);
-    if (!(v.global_row(ly, y) && x < v.W)) return;
+    const bool valid = v.global_row(ly, y) && x < v.W;
     const CamDev &cam = cams ? cams[blockIdx.z] : cam0;
-    float dx, dy, dz, sx, sy, sz;
-    primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
+    float dx = 0.0f, dy = 0.0f, dz = 1.0f, sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    if (valid) primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
     Hit h;
     TripCounts tc;
-    trace<World, false>(w, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+    trace<World, 0>(w, valid, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);  // all 32 lanes
     const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
     uint32_t albedo, normal, illum = 0u;
     float4 pos;
@@ -370,12 +374,15 @@ __global__ void __launch_bounds__(kThreads) frame_kernel(WorldArgs<World> wa, co
         normal = 0xFFFFFFFFu;
         pos = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
     }
-    if (!(pos.x < 0.0f || pos.y < 0.0f || pos.z < 0.0f)) {
+    {
+        const bool shoot = valid && !(pos.x < 0.0f || pos.y < 0.0f || pos.z < 0.0f);
         ViewDev vs = v;
         vs.max_steps = shadow_steps;
         uint32_t hit;
-        illum = shadow_pixel<World, false>(w, vs, pos.x, pos.y, pos.z, normal, tc, hit);
+        const uint32_t il = shadow_pixel<World, 0>(w, shoot, vs, pos.x, pos.y, pos.z, normal, tc, hit);  // all 32 lanes
+        if (shoot) illum = il;
     }
+    if (!valid) return;
     if (GBUF) {
         gb.albedo[i] = albedo;
         gb.normal[i] = normal;
@@ -396,7 +403,8 @@ __global__ void pick_kernel(WorldArgs<World> wa, CamDev cam, ViewDev v, uint8_t 
         stage_masks(s_masks, wa.masks);
         w.smem_masks = s_masks;
     }
-    if (threadIdx.x != 0) return;
+    const bool lead = threadIdx.x == 0;
+    if (threadIdx.x >= 32) return;  // one warp traces; lane 0 carries the ray
     float q[4];
     for (int i = 0; i < 4; ++i) {
         float acc = cam.mat[0 * 4 + i] * 0.0f;
@@ -413,8 +421,9 @@ __global__ void pick_kernel(WorldArgs<World> wa, CamDev cam, ViewDev v, uint8_t 
     const float t0 = gmax(tn, 0.0f);
     Hit h;
     TripCounts tc;
-    trace<World, false>(w, cam.pos[0] + dx * t0 - v.epsilon, cam.pos[1] + dy * t0 - v.epsilon, cam.pos[2] + dz * t0 - v.epsilon,
-                            dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+    trace<World, 0>(w, lead, cam.pos[0] + dx * t0 - v.epsilon, cam.pos[1] + dy * t0 - v.epsilon, cam.pos[2] + dz * t0 - v.epsilon,
+                    dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);
+    if (!lead) return;
     float dist = -1.0f;
     if (h.data != 0) {
         const float ex = h.hx / 8.0f - cam.pos[0], ey = h.hy / 8.0f - cam.pos[1], ez = h.hz / 8.0f - cam.pos[2];
@@ -485,8 +494,19 @@ __global__ void field_pass_kernel(const uint8_t *__restrict__ in, uint8_t *__res
     out[i] = (uint8_t)best;
 }
 
-// chunks2[(cd+1)^3]: bit 31 = empty chunk, low byte = n_free = max(8*(dist-1) - 2, 0); else 0-based brick index
-__global__ void build_chunks2_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ dist, uint32_t *__restrict__ chunks2, int cd) {
+// Empty chunks that touch a non-empty chunk (dist == 1) get a "virtual" brick: it holds no
+// material, only per-block clearances, so that rays skimming the terrain also get free trips.
+__global__ void count_virtual_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ dist, size_t n, unsigned int *counter) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool v = i < n && chunks[i] == 0 && dist[i] == 1;
+    const unsigned int m = __ballot_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31u) == 0 && m) atomicAdd(counter, (unsigned int)__popc(m));
+}
+
+// chunks2[(cd+1)^3]: bit 31 = far-empty chunk with low byte n_free = 8*(dist-1) - 2; else 0-based brick
+// index (real bricks keep the reference numbering, virtual bricks follow).  brick_chunk[b] = linear chunk index.
+__global__ void build_chunks2_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ dist, uint32_t *__restrict__ chunks2,
+                                     uint32_t *__restrict__ brick_chunk, int cd, uint32_t n_real, unsigned int *counter) {
     const int cd1 = cd + 1;
     const size_t n = (size_t)cd1 * cd1 * cd1;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -496,14 +516,84 @@ __global__ void build_chunks2_kernel(const uint32_t *__restrict__ chunks, const 
     if (x < cd && y < cd && z < cd) {
         const size_t j = (size_t)x + (size_t)cd * ((size_t)y + (size_t)z * cd);
         const uint32_t c = chunks[j];
-        if (c != 0) e = c - 1u;
-        else {
-            const int r = (int)dist[j] - 1;  // rings of empty in-map chunks around this one
-            const int nf = 8 * r - 2;
-            e = 0x80000000u | (uint32_t)min(max(nf, 0), 255);
+        if (c != 0) {
+            e = c - 1u;
+            brick_chunk[e] = (uint32_t)j;
+        } else if (dist[j] == 1) {
+            e = n_real + atomicAdd(counter, 1u);
+            brick_chunk[e] = (uint32_t)j;
+        } else {
+            const int r = (int)dist[j] - 1;  // rings of empty in-map chunks around this one (>= 1 here)
+            e = 0x80000000u | (uint32_t)min(max(8 * r - 2, 0), 255);
         }
     }
     chunks2[i] = e;
+}
+
+// rowmask[b][z][y] = 8 x-occupancy bits of brick b (material bytes only; clearances are not written yet)
+__global__ void brick_rowmask_kernel(const uint8_t *__restrict__ bricks8, size_t n_rows, uint8_t *__restrict__ rowmask) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const uint2 v = *reinterpret_cast<const uint2 *>(bricks8 + i * 8);
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if ((v.x >> (8 * k)) & 0xFFu) m |= 1u << k;
+        if ((v.y >> (8 * k)) & 0xFFu) m |= 1u << (k + 4);
+    }
+    rowmask[i] = (uint8_t)m;
+}
+
+// Block-level clearance.  One CTA per brick, one thread per block.  The occupancy of the 5x5x5 chunk
+// neighbourhood is staged in shared memory as 40x40 rows of 40 x-bits (out-of-map = occupied); each
+// empty block searches growing Chebyshev shells for the nearest occupied block, D capped at 16, and
+// stores kMatLimit + max(D - 3, 0).
+constexpr int kClearCap = 16;
+__global__ void __launch_bounds__(512) clearance_kernel(const uint32_t *__restrict__ chunks2, int cd, const uint32_t *__restrict__ brick_chunk,
+                                                        const uint8_t *__restrict__ rowmask, uint8_t *__restrict__ bricks8) {
+    __shared__ unsigned long long rows[40 * 40];  // [z'][y'], bit i = x' = i - 16 relative to the brick origin
+    const uint32_t b = blockIdx.x;
+    const uint32_t cj = brick_chunk[b];
+    const int cx = (int)(cj % cd), cy = (int)((cj / cd) % cd), cz = (int)(cj / ((uint32_t)cd * cd));
+    const int cd1 = cd + 1;
+    for (int r = threadIdx.x; r < 40 * 40; r += blockDim.x) {
+        const int yy = r % 40, zz = r / 40;                 // 0..39 -> block offset -16..23
+        const int ncy = cy + (yy >> 3) - 2, ncz = cz + (zz >> 3) - 2;
+        unsigned long long bits = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int ncx = cx + k - 2;
+            uint32_t m8;
+            if (ncx < 0 || ncy < 0 || ncz < 0 || ncx >= cd || ncy >= cd || ncz >= cd) m8 = 0xFFu;  // outside the map
+            else {
+                const uint32_t e = chunks2[(size_t)ncx + (size_t)cd1 * ((size_t)ncy + (size_t)ncz * cd1)];
+                m8 = ((int)e < 0) ? 0u : rowmask[(size_t)e * 64u + (size_t)(zz & 7) * 8u + (size_t)(yy & 7)];
+            }
+            bits |= (unsigned long long)m8 << (8 * k);
+        }
+        rows[r] = bits;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7, lz = threadIdx.x >> 6;
+    const size_t addr = (size_t)b * 512u + threadIdx.x;
+    if (bricks8[addr] != 0) return;  // material block
+    const int x0 = lx + 16, y0 = ly + 16, z0 = lz + 16;
+    int D = kClearCap;
+    for (int r = 1; r < kClearCap; ++r) {
+        const unsigned long long range = ((1ull << (2 * r + 1)) - 1ull) << (x0 - r);
+        const unsigned long long ends = (1ull << (x0 - r)) | (1ull << (x0 + r));
+        bool found = false;
+        for (int dz = -r; dz <= r && !found; ++dz) {
+            const bool zedge = dz == -r || dz == r;
+            const unsigned long long *row = &rows[(z0 + dz) * 40 + y0];
+            for (int dy = -r; dy <= r; ++dy) {
+                const unsigned long long m = (zedge || dy == -r || dy == r) ? range : ends;  // only the new shell
+                if (row[dy] & m) { found = true; break; }
+            }
+        }
+        if (found) { D = r; break; }
+    }
+    bricks8[addr] = (uint8_t)(kMatLimit + max(D - 3, 0));
 }
 
 // ---- bandwidth probes (roofline denominators) ----------------------------------

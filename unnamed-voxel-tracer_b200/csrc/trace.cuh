@@ -78,6 +78,7 @@ struct WorldCompact {
     const uint32_t *smem_masks;             // [256][16] shared-memory copy of the occupancy masks
     uint32_t cd;
     uint32_t cd1;                           // cd + 1: stride of chunks2 (one guard layer on the high side)
+    uint32_t n_real_bricks;                 // bricks [0, n_real) mirror reference bricks; the rest only carry clearances
 
     __device__ __forceinline__ uint32_t block_at(uint32_t px, uint32_t py, uint32_t pz, bool &chunk_hit) const {
         const uint32_t bx = px >> 3, by = py >> 3, bz = pz >> 3;
@@ -196,28 +197,38 @@ __device__ __forceinline__ void trace_map(const World &w, float ox, float oy, fl
 }
 
 // ---- traceMap, B200 fast path ----------------------------------------------------------
-// Same trips, same arithmetic as trace_map (map.glsl:83-168); what changes is what is FETCHED:
+// Same trips, same arithmetic as trace_map (map.glsl:83-168); what changes is what is FETCHED
+// and how the loop is laid out:
 //
-//  * chunks2[(cd+1)^3] marks empty chunks with bit 31 and carries in its low byte n_free, the
-//    number of FOLLOWING trips that are guaranteed to (a) stay inside the map and (b) look up
-//    an empty block, derived from the Chebyshev distance (in chunks) to the nearest non-empty
-//    chunk or map face (build_chunk_field_*).  Such trips run the DDA arithmetic only — no
-//    bounds test, no `pos`, no loads.  Proof of the bound: at 8-sub-voxel steps g moves exactly
-//    one block along one axis per trip, `pos` is within one block of g (within in [-1, 8+ulp]),
-//    so after j trips the looked-up block is within j+2 blocks of the block looked up now; with
-//    R empty in-map chunk rings around this chunk every block within 8R is empty, hence
-//    n_free = 8R - 2.
+//  * FREE TRIPS.  chunks2[(cd+1)^3] marks far-empty chunks with bit 31 and carries n_free in its
+//    low byte; every other chunk (non-empty, or empty but touching a non-empty one) owns a brick
+//    of one byte per block: < kMatLimit = material id, >= kMatLimit = empty with
+//    n_free = byte - kMatLimit.  n_free is the number of FOLLOWING trips that provably (a) stay
+//    inside the map and (b) look up an empty block, so they run the DDA arithmetic only — no
+//    bounds test, no `pos`, no loads.  Proof: at 8-sub-voxel steps g moves exactly one block along
+//    one axis per trip and `pos` is in g's block or, when a `within` component rounds up to 8, one
+//    block further; with D the Chebyshev distance (blocks) from the looked-up block to the nearest
+//    non-empty block or map face, trips j <= D - 3 look up blocks within j + 2 < D of it.  The
+//    chunk-level field gives D >= 8R + 1 for R empty chunk rings, hence n_free = 8R - 2 there;
+//    the block-level field (clearance kernel) gives n_free = min(D, 8) - 3 inside bricks.
+//    (COUNT instantiations ignore n_free so that the reference counters stay exact.)
+//  * at block steps with within < 8 the block holding `pos` is g >> 3, so the float->int
+//    conversions of map.glsl:108 are skipped until a non-empty block is found.
 //  * the guard layer of chunks2 (index cd on any axis) removes the chunk-range test: `pos` can
 //    exceed the map by at most one block on the high side while g is in bounds.
-//  * bricks hold one byte per block; sub-voxel occupancy is a bit test in shared memory; colour
-//    and block word are fetched once, at the hit.
-//  * per-phase constants (target face, reset value, signed step per axis) are kept in registers
-//    and rewritten only when the step size changes.
+//  * sub-voxel occupancy is a bit test in shared memory; colour and block word are fetched once,
+//    at the hit.  Per-phase constants (target face, reset value, signed step per axis) live in
+//    registers and are rewritten only when the step size changes.
+//  * the loop is rotated (DDA step first, then the next trip's lookup) so that the min-axis
+//    predicates are still live when a hit needs them for the face id.
 //
 // Rays with non-finite reciprocals or origins beyond 2^20 sub-voxels take the generic path,
 // whose corner-case behaviour (NaN ordering, saturation) is the specification.
-template <bool COUNT>
-__device__ __forceinline__ void trace_map_fast(const WorldCompact &w, float ox, float oy, float oz, float dx, float dy, float dz,
+constexpr uint32_t kMatLimit = 224;  // brick bytes >= kMatLimit encode empty blocks
+
+// Must be called by ALL 32 lanes of a warp (it uses full-mask warp votes); `active` = this lane has a ray.
+template <int COUNT>
+__device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool active, float ox, float oy, float oz, float dx, float dy, float dz,
                                                int max_steps, int bound, Hit &out, TripCounts &tc) {
     if (dx == 0.0f) dx = 0.001f;
     if (dy == 0.0f) dy = 0.001f;
@@ -227,10 +238,12 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, float ox, 
     const bool sane = fabsf(invx) < 1e30f && fabsf(invy) < 1e30f && fabsf(invz) < 1e30f &&
                       fabsf(dx) < 1e30f && fabsf(dy) < 1e30f && fabsf(dz) < 1e30f &&
                       fabsf(o8x) < 1048576.0f && fabsf(o8y) < 1048576.0f && fabsf(o8z) < 1048576.0f;
-    if (!sane) {
-        trace_map<WorldCompact, COUNT>(w, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
-        return;
+    const bool generic = active && (!sane || max_steps <= 0);
+    if (generic) {  // rare lanes: the generic loop is the specification for corner cases
+        trace_map<WorldCompact, COUNT == 1>(w, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
+        if (COUNT == 2) tc.t_in = tc.t_chunk = tc.t_block = 0;
     }
+    const bool fast = active && !generic;
     const bool posx = dx > 0.0f, posy = dy > 0.0f, posz = dz > 0.0f;
 
     int gx = __float2int_rz(o8x), gy = __float2int_rz(o8y), gz = __float2int_rz(o8z);
@@ -241,105 +254,149 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, float ox, 
     float rsx = posx ? 0.0f : 0.999f, rsy = posy ? 0.0f : 0.999f, rsz = posz ? 0.0f : 0.999f;    // float((1 - pos) << step) * 0.999f
     int isx = posx ? 1 : -1, isy = posy ? 1 : -1, isz = posz ? 1 : -1;                           // raySign << step
     bool big = false;
-    bool mx = true, my = false;  // minIdx == 0 / == 1 of the previous trip (initially 0)
-    int free_trips = 0;
 
-    out.data = 0;
-    out.hx = out.hy = out.hz = -1.0f;
-    out.px = out.py = out.pz = 0xFFFFFFFFu;
-    out.block = 0;
-    out.face = 0;
-    out.exit_kind = 1;
-    if (COUNT) tc.t_in = tc.t_chunk = tc.t_block = 0;
+    if (!generic) {
+        out.data = 0;
+        out.hx = out.hy = out.hz = -1.0f;
+        out.px = out.py = out.pz = 0xFFFFFFFFu;
+        out.block = 0;
+        out.face = 0;
+        out.exit_kind = 1;
+        out.trips = 0;
+        if (COUNT) tc.t_in = tc.t_chunk = tc.t_block = 0;
+    }
 
     const uint32_t cd1 = w.cd1;
-    int trip = 0;
-    for (; trip < max_steps; ++trip) {
-        if (free_trips > 0) {
-            --free_trips;
-            if (COUNT) tc.t_in++;
-        } else {
-            if ((unsigned)gx >= (unsigned)bound || (unsigned)gy >= (unsigned)bound || (unsigned)gz >= (unsigned)bound) {
-                out.exit_kind = 2;
-                break;
-            }
-            if (COUNT) tc.t_in++;
-            const uint32_t px = (uint32_t)gx + __float2uint_rz(wx);
-            const uint32_t py = (uint32_t)gy + __float2uint_rz(wy);
-            const uint32_t pz = (uint32_t)gz + __float2uint_rz(wz);
-            const uint32_t e = __ldg(&w.chunks2[(px >> 6) + cd1 * ((py >> 6) + (pz >> 6) * cd1)]);
-            uint32_t mat = 0;
-            if ((int)e < 0) {
-                free_trips = (int)(e & 0xFFu);
-            } else {
-                if (COUNT) tc.t_chunk++;
-                mat = __ldg(&w.bricks8[(size_t)e * 512u + (((px >> 3) & 7u) | (py & 0x38u) | ((pz & 0x38u) << 3))]);
-            }
-            if (mat != 0) {
-                if (COUNT) tc.t_block++;
-                const uint32_t bit = (px & 7u) | ((py & 7u) << 3) | ((pz & 7u) << 6);
-                const uint32_t word = w.smem_masks[mat * 16u + (bit >> 5)];
-                if ((word >> (bit & 31u)) & 1u) {
-                    out.data = __ldg(&w.mat_color[mat * 512u + bit]);
-                    out.face = mx ? (posx ? 1u : 2u) : (my ? (posy ? 3u : 4u) : (posz ? 5u : 6u));
-                    out.hx = (float)gx + wx;
-                    out.hy = (float)gy + wy;
-                    out.hz = (float)gz + wz;
-                    out.px = px; out.py = py; out.pz = pz;
-                    out.block = __ldg(&w.mat_word[mat]);
-                    out.exit_kind = 0;
-                    out.trips = (uint32_t)trip + 1u;
-                    return;
-                }
-                if (big) {  // drop to sub-voxel steps (map.glsl:131-135)
-                    gx += __float2int_rz(wx);
-                    gy += __float2int_rz(wy);
-                    gz += __float2int_rz(wz);
-                    wx = wx - floorf(wx);
-                    wy = wy - floorf(wy);
-                    wz = wz - floorf(wz);
-                    big = false;
-                    tgx = posx ? 1.0f : 0.0f; tgy = posy ? 1.0f : 0.0f; tgz = posz ? 1.0f : 0.0f;
-                    rsx = posx ? 0.0f : 0.999f; rsy = posy ? 0.0f : 0.999f; rsz = posz ? 0.0f : 0.999f;
-                    isx = posx ? 1 : -1; isy = posy ? 1 : -1; isz = posz ? 1 : -1;
-                }
-            } else if (!big) {  // rise to block steps (map.glsl:140-144)
-                wx += (float)(gx & 7);
-                wy += (float)(gy & 7);
-                wz += (float)(gz & 7);
-                gx &= ~7;
-                gy &= ~7;
-                gz &= ~7;
-                big = true;
-                tgx = posx ? 8.0f : 0.0f; tgy = posy ? 8.0f : 0.0f; tgz = posz ? 8.0f : 0.0f;
-                rsx = posx ? 0.0f : 8.0f * 0.999f; rsy = posy ? 0.0f : 8.0f * 0.999f; rsz = posz ? 0.0f : 8.0f * 0.999f;
-                isx = posx ? 8 : -8; isy = posy ? 8 : -8; isz = posz ? 8 : -8;
-            }
-        }
+    int trip = 0;   // warp-uniform
+    int limit = 0;  // trips in [trip, limit) need no lookup
 
-        // dda stepping (map.glsl:157-162)
-        const float tx = (tgx - wx) * invx;
-        const float ty = (tgy - wy) * invy;
-        const float tz = (tgz - wz) * invz;
-        mx = (tx < ty) && (tx < tz);
-        my = !(tx < ty) && (ty < tz);
-        const float tm = mx ? tx : (my ? ty : tz);
-        wx += dx * tm;
-        wy += dy * tm;
-        wz += dz * tm;
-        if (mx) { gx += isx; wx = rsx; }
-        else if (my) { gy += isy; wy = rsy; }
-        else { gz += isz; wz = rsz; }
+    // Everything a trip does before its DDA step (map.glsl:107-144).  lastx/lasty: minIdx of the
+    // previous trip was 0 / 1.  Returns false when the ray ends here.
+    auto visit = [&](bool lastx, bool lasty) -> bool {
+        if ((unsigned)gx >= (unsigned)bound || (unsigned)gy >= (unsigned)bound || (unsigned)gz >= (unsigned)bound) {
+            out.exit_kind = 2;
+            out.trips = (uint32_t)trip;
+            return false;
+        }
+        if (COUNT == 2) tc.t_in++;  // lookups performed
+        uint32_t px = (uint32_t)gx, py = (uint32_t)gy, pz = (uint32_t)gz;
+        // at block steps g is a multiple of 8; with within < 8 the block of `pos` is g >> 3
+        const bool lazy = big && fmaxf(fmaxf(wx, wy), wz) < 8.0f;
+        if (!lazy) {
+            px += __float2uint_rz(wx);
+            py += __float2uint_rz(wy);
+            pz += __float2uint_rz(wz);
+        }
+        const uint32_t e = __ldg(&w.chunks2[(px >> 6) + cd1 * ((py >> 6) + (pz >> 6) * cd1)]);
+        uint32_t mat = 0;
+        int n_free;
+        if ((int)e < 0) {
+            n_free = (int)(e & 0xFFu);
+        } else {
+            if (COUNT == 1 && e < w.n_real_bricks) tc.t_chunk++;
+            const uint32_t b = __ldg(&w.bricks8[e * 512u + (((px >> 3) & 7u) | (py & 0x38u) | ((pz & 0x38u) << 3))]);
+            n_free = (int)b - (int)kMatLimit;
+            if (n_free < 0) { mat = b; n_free = 0; }
+        }
+        if (COUNT == 1) n_free = 0;  // exact reference counters need every trip's lookup
+        limit = trip + 1 + n_free;
+        if (mat != 0) {
+            if (COUNT == 1) tc.t_block++;
+            if (lazy) {
+                px += __float2uint_rz(wx);
+                py += __float2uint_rz(wy);
+                pz += __float2uint_rz(wz);
+            }
+            const uint32_t bit = (px & 7u) | ((py & 7u) << 3) | ((pz & 7u) << 6);
+            const uint32_t word = w.smem_masks[mat * 16u + (bit >> 5)];
+            if ((word >> (bit & 31u)) & 1u) {
+                out.data = __ldg(&w.mat_color[mat * 512u + bit]);
+                out.face = lastx ? (posx ? 1u : 2u) : (lasty ? (posy ? 3u : 4u) : (posz ? 5u : 6u));
+                out.hx = (float)gx + wx;
+                out.hy = (float)gy + wy;
+                out.hz = (float)gz + wz;
+                out.px = px; out.py = py; out.pz = pz;
+                out.block = __ldg(&w.mat_word[mat]);
+                out.exit_kind = 0;
+                out.trips = (uint32_t)trip + 1u;
+                return false;
+            }
+            if (big) {  // drop to sub-voxel steps (map.glsl:131-135)
+                gx += __float2int_rz(wx);
+                gy += __float2int_rz(wy);
+                gz += __float2int_rz(wz);
+                wx = wx - floorf(wx);
+                wy = wy - floorf(wy);
+                wz = wz - floorf(wz);
+                big = false;
+                tgx = posx ? 1.0f : 0.0f; tgy = posy ? 1.0f : 0.0f; tgz = posz ? 1.0f : 0.0f;
+                rsx = posx ? 0.0f : 0.999f; rsy = posy ? 0.0f : 0.999f; rsz = posz ? 0.0f : 0.999f;
+                isx = posx ? 1 : -1; isy = posy ? 1 : -1; isz = posz ? 1 : -1;
+            }
+        } else if (!big) {  // rise to block steps (map.glsl:140-144)
+            wx += (float)(gx & 7);
+            wy += (float)(gy & 7);
+            wz += (float)(gz & 7);
+            gx &= ~7;
+            gy &= ~7;
+            gz &= ~7;
+            big = true;
+            tgx = posx ? 8.0f : 0.0f; tgy = posy ? 8.0f : 0.0f; tgz = posz ? 8.0f : 0.0f;
+            rsx = posx ? 0.0f : 8.0f * 0.999f; rsy = posy ? 0.0f : 8.0f * 0.999f; rsz = posz ? 0.0f : 8.0f * 0.999f;
+            isx = posx ? 8 : -8; isy = posy ? 8 : -8; isz = posz ? 8 : -8;
+        }
+        return true;
+    };
+
+    // Warp-lockstep schedule: all lanes of the warp are at the same trip index.  After a round of
+    // lookups every live lane knows how many of its next trips are free; the warp runs the minimum
+    // of those as a divergence-free DDA loop (uniform trip count), then looks up again together.
+    // Lanes whose ray has ended keep executing the arithmetic on dead state (no memory traffic).
+    bool alive = fast;
+    if (alive) alive = visit(true, false);  // trip 0: minIdx starts at 0 (map.glsl:98)
+    bool mx = true, my = false;
+    for (;;) {
+        const unsigned live = __ballot_sync(0xFFFFFFFFu, alive);
+        if (live == 0u) break;
+        int k = __reduce_min_sync(0xFFFFFFFFu, alive ? limit - trip : 0x7FFFFFFF);
+        k = min(k, max_steps - trip);  // max_steps > 0 on every live lane
+        for (int j = 0; j < k; ++j) {
+            // dda stepping (map.glsl:157-162)
+            const float tx = (tgx - wx) * invx;
+            const float ty = (tgy - wy) * invy;
+            const float tz = (tgz - wz) * invz;
+            const bool xy = tx < ty;
+            mx = xy && (tx < tz);
+            my = !xy && (ty < tz);
+            const float tm = mx ? tx : (my ? ty : tz);
+            wx += dx * tm;
+            wy += dy * tm;
+            wz += dz * tm;
+            if (mx) { gx += isx; wx = rsx; }
+            else if (my) { gy += isy; wy = rsy; }
+            else { gz += isz; wz = rsz; }
+        }
+        trip += k;
+        if (trip >= max_steps) {  // iteration cap: miss (map.glsl:167)
+            if (alive) out.trips = (uint32_t)trip;
+            break;
+        }
+        if (alive) alive = visit(mx, my);
     }
-    out.trips = (uint32_t)trip;
+    if (COUNT == 1 && fast) tc.t_in = out.trips;  // every executed trip passed the bounds test
 }
 
 // dispatch: the compact world takes the fast path
-template <class World, bool COUNT>
-__device__ __forceinline__ void trace(const World &w, float ox, float oy, float oz, float dx, float dy, float dz,
+// COUNT: 0 none, 1 exact reference counters (t_in, t_chunk, t_block), 2 fast-path statistics (t_in = lookups performed)
+// Must be called by all 32 lanes of a warp; lanes without a ray pass active = false.
+template <class World, int COUNT>
+__device__ __forceinline__ void trace(const World &w, bool active, float ox, float oy, float oz, float dx, float dy, float dz,
                                       int max_steps, int bound, Hit &out, TripCounts &tc) {
-    if constexpr (std::is_same<World, WorldCompact>::value) trace_map_fast<COUNT>(w, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
-    else trace_map<World, COUNT>(w, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
+    if constexpr (std::is_same<World, WorldCompact>::value) trace_map_fast<COUNT>(w, active, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
+    else if (active) {
+        trace_map<World, COUNT == 1>(w, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
+        if (COUNT == 2) tc.t_in = tc.t_chunk = tc.t_block = 0;
+    }
 }
 
 }  // namespace uvt

@@ -47,6 +47,7 @@ struct uvt_ctx {
     uint8_t *d_bricks8 = nullptr;
     size_t d_brick8_capacity = 0;
     uint32_t *d_chunks2 = nullptr;  // fast-path chunk table [(cd+1)^3]
+    size_t n_total_bricks = 0;      // real + virtual (clearance-only) bricks in d_bricks8
     bool world_committed = false;
 
     // ---- atlas: host copy by slot (slot = x/8 + 32*(y/8) + 1024*(z/8)), device [n_slots][512]
@@ -236,6 +237,7 @@ WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     a.w.chunks = c->d_chunks;
     a.w.chunks2 = c->d_chunks2;
     a.w.cd1 = c->cd + 1;
+    a.w.n_real_bricks = (uint32_t)c->n_bricks;
     a.w.bricks8 = c->d_bricks8;
     a.w.mat_word = c->d_mat_word;
     a.w.mat_color = c->d_mat_color;
@@ -304,7 +306,7 @@ int pre_dispatch(uvt_ctx *c) {
     return ensure_ready(c);
 }
 
-template <bool COUNT>
+template <int COUNT>
 int launch_primary(uvt_ctx *c) {
     const ViewDev v = make_view(c, c->params.primary_max_steps);
     const GBufDev g = make_gbuf(c);
@@ -323,7 +325,7 @@ int launch_primary(uvt_ctx *c) {
     return check_launch(c, "primary_kernel");
 }
 
-template <bool COUNT>
+template <int COUNT>
 int launch_secondary(uvt_ctx *c) {
     const ViewDev v = make_view(c, c->params.shadow_max_steps);
     const GBufDev g = make_gbuf(c);
@@ -331,6 +333,93 @@ int launch_secondary(uvt_ctx *c) {
     if (use_compact(c)) secondary_kernel<WorldCompact, COUNT><<<grid, kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
     else secondary_kernel<WorldRef, COUNT><<<grid, kThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
     return check_launch(c, "secondary_kernel");
+}
+
+// Build the B200 layout from the committed reference layout (all on the device):
+// chunk distance field -> virtual bricks -> chunks2, 8-bit material bricks, block clearances.
+int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
+    const int cd = (int)c->cd;
+    const size_t n_chunks = (size_t)cd * cd * cd;
+    const size_t n2 = (size_t)(cd + 1) * (cd + 1) * (cd + 1);
+    uint8_t *f0 = nullptr, *f1 = nullptr, *rowmask = nullptr, *d_vals = nullptr;
+    uint32_t *d_keys = nullptr, *brick_chunk = nullptr;
+    unsigned int *d_counter = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(f0); cudaFree(f1); cudaFree(rowmask); cudaFree(d_vals); cudaFree(d_keys); cudaFree(brick_chunk); cudaFree(d_counter);
+    };
+#define UVT_CUDA_C(expr)                                                                                      \
+    do {                                                                                                      \
+        cudaError_t e_ = (expr);                                                                              \
+        if (e_ != cudaSuccess) {                                                                              \
+            cleanup();                                                                                        \
+            return set_error(c, e_ == cudaErrorMemoryAllocation ? UVT_ERR_OOM : UVT_ERR_CUDA, "%s: %s (%s:%d)", \
+                             #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
+        }                                                                                                     \
+    } while (0)
+    UVT_CUDA_C(cudaMalloc(&f0, n_chunks));
+    UVT_CUDA_C(cudaMalloc(&f1, n_chunks));
+    UVT_CUDA_C(cudaMalloc(&d_counter, 4));
+    const unsigned cblocks = (unsigned)((n_chunks + 255) / 256);
+    field_pass_x_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, cd);
+    field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(f0, f1, cd, (size_t)cd);
+    field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(f1, f0, cd, (size_t)cd * cd);
+    UVT_CUDA_C(cudaMemsetAsync(d_counter, 0, 4, c->stream));
+    count_virtual_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, n_chunks, d_counter);
+    unsigned int n_virtual = 0;
+    UVT_CUDA_C(cudaMemcpyAsync(&n_virtual, d_counter, 4, cudaMemcpyDeviceToHost, c->stream));
+    UVT_CUDA_C(cudaStreamSynchronize(c->stream));
+    c->launches += 4;
+    const size_t n_total = n_bricks + n_virtual;
+    if (n_total * 512 >= (1ull << 32)) {  // brick byte offsets are 32-bit in the traversal kernel
+        cleanup();
+        c->compact_ok = false;
+        return UVT_OK;
+    }
+    if (std::max<size_t>(n_total, 1) > c->d_brick8_capacity) {
+        cudaFree(c->d_bricks8);
+        c->d_bricks8 = nullptr;
+        const size_t want = std::max<size_t>(n_total + n_total / 4, 64);
+        UVT_CUDA_C(cudaMalloc(&c->d_bricks8, want * 512));
+        c->d_brick8_capacity = want;
+    }
+    UVT_CUDA_C(cudaMalloc(&brick_chunk, std::max<size_t>(n_total, 1) * 4));
+    UVT_CUDA_C(cudaMemsetAsync(d_counter, 0, 4, c->stream));
+    build_chunks2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(c->d_chunks, f0, c->d_chunks2, brick_chunk, cd, (uint32_t)n_bricks, d_counter);
+    c->launches++;
+    if (n_total) {
+        UVT_CUDA_C(cudaMemsetAsync(c->d_bricks8, 0, n_total * 512, c->stream));
+        if (n_bricks) {
+            // open-addressed block word -> material id table for the repack kernel
+            const uint32_t lut_size = 1024, lut_mask = lut_size - 1;
+            std::vector<uint32_t> keys(lut_size, 0);
+            std::vector<uint8_t> vals(lut_size, 0);
+            for (size_t m = 1; m < c->mat_words.size(); ++m) {
+                uint32_t h = (c->mat_words[m] * 2654435761u) & lut_mask;
+                while (keys[h] != 0) h = (h + 1) & lut_mask;
+                keys[h] = c->mat_words[m];
+                vals[h] = (uint8_t)m;
+            }
+            UVT_CUDA_C(cudaMalloc(&d_keys, lut_size * 4));
+            UVT_CUDA_C(cudaMalloc(&d_vals, lut_size));
+            UVT_CUDA_C(cudaMemcpyAsync(d_keys, keys.data(), lut_size * 4, cudaMemcpyHostToDevice, c->stream));
+            UVT_CUDA_C(cudaMemcpyAsync(d_vals, vals.data(), lut_size, cudaMemcpyHostToDevice, c->stream));
+            repack_bricks_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_bricks, c->d_bricks8, n_words, d_keys, d_vals, lut_mask);
+            c->launches++;
+            UVT_CUDA_C(cudaStreamSynchronize(c->stream));  // keys/vals staging dies at scope exit
+        }
+        UVT_CUDA_C(cudaMalloc(&rowmask, n_total * 64));
+        const size_t n_rows = n_total * 64;
+        brick_rowmask_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, c->stream>>>(c->d_bricks8, n_rows, rowmask);
+        clearance_kernel<<<(unsigned)n_total, 512, 0, c->stream>>>(c->d_chunks2, cd, brick_chunk, rowmask, c->d_bricks8);
+        c->launches += 2;
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+#undef UVT_CUDA_C
+    if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "building the compact layout failed: %s", cudaGetErrorString(e));
+    c->n_total_bricks = n_total;
+    return UVT_OK;
 }
 
 }  // namespace
@@ -452,8 +541,8 @@ int uvt_pipeline_create(uvt_ctx *c, uvt_pipeline_kind kind, uvt_pipeline **out) 
     cudaFuncAttributes fa;
     const void *fn = nullptr;
     switch (kind) {
-        case UVT_PIPELINE_PRIMARY: fn = (const void *)primary_kernel<WorldCompact, false, false>; break;
-        case UVT_PIPELINE_SECONDARY: fn = (const void *)secondary_kernel<WorldCompact, false>; break;
+        case UVT_PIPELINE_PRIMARY: fn = (const void *)primary_kernel<WorldCompact, 0, false>; break;
+        case UVT_PIPELINE_SECONDARY: fn = (const void *)secondary_kernel<WorldCompact, 0>; break;
         case UVT_PIPELINE_EDIT: fn = (const void *)pick_kernel<WorldCompact>; break;
         case UVT_PIPELINE_BLIT: fn = (const void *)shade_kernel; break;
     }
@@ -558,63 +647,14 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
         if (wd == 0 || wd == last_word) continue;
         last_word = wd;
         if (ids.find(wd) == ids.end()) {
-            if (c->mat_words.size() >= 256) { overflow = true; break; }
+            if (c->mat_words.size() >= kMatLimit) { overflow = true; break; }  // ids >= kMatLimit encode clearances
             ids.emplace(wd, (uint32_t)c->mat_words.size());
             c->mat_words.push_back(wd);
         }
     }
     c->compact_ok = !overflow;
     if (c->compact_ok) {
-        if (cap > c->d_brick8_capacity) {
-            cudaFree(c->d_bricks8);
-            c->d_bricks8 = nullptr;
-            const size_t want = std::max(cap, c->h_capacity);
-            UVT_CUDA(c, cudaMalloc(&c->d_bricks8, want * 512));
-            c->d_brick8_capacity = want;
-        }
-        if (n_bricks) {
-            // open-addressed word -> id table for the repack kernel
-            const uint32_t lut_size = 1024, lut_mask = lut_size - 1;
-            std::vector<uint32_t> keys(lut_size, 0);
-            std::vector<uint8_t> vals(lut_size, 0);
-            for (size_t m = 1; m < c->mat_words.size(); ++m) {
-                uint32_t h = (c->mat_words[m] * 2654435761u) & lut_mask;
-                while (keys[h] != 0) h = (h + 1) & lut_mask;
-                keys[h] = c->mat_words[m];
-                vals[h] = (uint8_t)m;
-            }
-            uint32_t *d_keys = nullptr;
-            uint8_t *d_vals = nullptr;
-            UVT_CUDA(c, cudaMalloc(&d_keys, lut_size * 4));
-            UVT_CUDA(c, cudaMalloc(&d_vals, lut_size));
-            UVT_CUDA(c, cudaMemcpyAsync(d_keys, keys.data(), lut_size * 4, cudaMemcpyHostToDevice, c->stream));
-            UVT_CUDA(c, cudaMemcpyAsync(d_vals, vals.data(), lut_size, cudaMemcpyHostToDevice, c->stream));
-            const int blocks = c->sm_count * 8;
-            repack_bricks_kernel<<<blocks, 256, 0, c->stream>>>(c->d_bricks, c->d_bricks8, n_words, d_keys, d_vals, lut_mask);
-            int rc = check_launch(c, "repack_bricks_kernel");
-            cudaStreamSynchronize(c->stream);
-            cudaFree(d_keys);
-            cudaFree(d_vals);
-            if (rc != UVT_OK) return rc;
-        }
-    }
-    if (c->compact_ok) {
-        // chunk distance field -> fast-path chunk table
-        const int cd = (int)c->cd;
-        uint8_t *f0 = nullptr, *f1 = nullptr;
-        UVT_CUDA(c, cudaMalloc(&f0, n_chunks));
-        UVT_CUDA(c, cudaMalloc(&f1, n_chunks));
-        const unsigned blocks = (unsigned)((n_chunks + 255) / 256);
-        field_pass_x_kernel<<<blocks, 256, 0, c->stream>>>(c->d_chunks, f0, cd);
-        field_pass_kernel<<<blocks, 256, 0, c->stream>>>(f0, f1, cd, (size_t)cd);
-        field_pass_kernel<<<blocks, 256, 0, c->stream>>>(f1, f0, cd, (size_t)cd * cd);
-        const size_t n2 = (size_t)(cd + 1) * (cd + 1) * (cd + 1);
-        build_chunks2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(c->d_chunks, f0, c->d_chunks2, cd);
-        int rc = check_launch(c, "chunk field kernels");
-        c->launches += 3;
-        cudaStreamSynchronize(c->stream);
-        cudaFree(f0);
-        cudaFree(f1);
+        int rc = build_compact(c, n_bricks, n_words);
         if (rc != UVT_OK) return rc;
     }
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -711,7 +751,7 @@ int uvt_dispatch_primary(uvt_ctx *c) {
     int rc = pre_dispatch(c);
     if (rc != UVT_OK) return rc;
     PassTimer t(c, 0);
-    return launch_primary<false>(c);
+    return launch_primary<0>(c);
 }
 
 int uvt_dispatch_secondary(uvt_ctx *c) {
@@ -719,7 +759,7 @@ int uvt_dispatch_secondary(uvt_ctx *c) {
     int rc = pre_dispatch(c);
     if (rc != UVT_OK) return rc;
     PassTimer t(c, 1);
-    return launch_secondary<false>(c);
+    return launch_secondary<0>(c);
 }
 
 int uvt_shade(uvt_ctx *c) {
@@ -831,11 +871,11 @@ int uvt_free_pinned(uvt_ctx *c, void *p) {
 
 int uvt_count_pass(uvt_ctx *c, int which, uvt_counters *out) {
     if (!c || !out) return UVT_ERR_INVALID;
-    UVT_REQUIRE(c, which == 0 || which == 1, "which must be 0 (primary) or 1 (secondary)");
+    UVT_REQUIRE(c, which >= 0 && which <= 3, "which must be 0/1 (reference counters) or 2/3 (fast-path fetch statistics) for primary/secondary");
     int rc = pre_dispatch(c);
     if (rc != UVT_OK) return rc;
     UVT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), c->stream));
-    rc = which == 0 ? launch_primary<true>(c) : launch_secondary<true>(c);
+    rc = which == 0 ? launch_primary<1>(c) : (which == 1 ? launch_secondary<1>(c) : (which == 2 ? launch_primary<2>(c) : launch_secondary<2>(c)));
     if (rc != UVT_OK) return rc;
     DevCounters h;
     UVT_CUDA(c, cudaMemcpyAsync(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));

@@ -183,6 +183,12 @@ class Context:
         self.check(self.L.uvt_count_pass(self.handle, 0 if which == "primary" else 1, ctypes.byref(c)))
         return c.as_dict()
 
+    def fetch_stats(self, which):
+        """Fast-path statistics of one pass: {'rays', 'lookups'} — trips that actually fetched world data."""
+        c = N.Counters()
+        self.check(self.L.uvt_count_pass(self.handle, 2 if which == "primary" else 3, ctypes.byref(c)))
+        return {"rays": int(c.rays), "lookups": int(c.t_in), "hits": int(c.hits)}
+
     def enable_timing(self, on=True):
         self.check(self.L.uvt_enable_timing(self.handle, 1 if on else 0))
 
