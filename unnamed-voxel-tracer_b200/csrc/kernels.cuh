@@ -170,8 +170,9 @@ __device__ __forceinline__ void tile_pixel(uint32_t &x, uint32_t &ly) {
     ly = blockIdx.y * kTileH + (warp >> 1) * 4u + (lane >> 3);
 }
 
-__device__ __forceinline__ void stage_masks(uint32_t *smem, const uint32_t *__restrict__ gmasks) {
-    for (uint32_t i = threadIdx.x; i < 256u * 16u; i += blockDim.x) smem[i] = __ldg(&gmasks[i]);
+__device__ __forceinline__ void stage_masks(uint32_t *smem, const uint32_t *__restrict__ gmasks, uint32_t n_mats) {
+    // only the materials in use: (n_mats + 1) x 16 words (id 0 is the empty block)
+    for (uint32_t i = threadIdx.x; i < (n_mats + 1u) * 16u; i += blockDim.x) smem[i] = __ldg(&gmasks[i]);
     __syncthreads();
 }
 
@@ -182,11 +183,13 @@ template <>
 struct WorldArgs<WorldRef> {
     WorldRef w;
     const uint32_t *masks;  // unused
+    uint32_t n_mats;
 };
 template <>
 struct WorldArgs<WorldCompact> {
     WorldCompact w;
     const uint32_t *masks;  // global [256][16]
+    uint32_t n_mats;        // material ids in use: 1..n_mats
 };
 
 // ---- primary pass ------------------------------------------------------------------------
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) primary_kernel(WorldArgs<World> wa, 
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
     World w = wa.w;
     if constexpr (std::is_same<World, WorldCompact>::value) {
-        stage_masks(s_masks, wa.masks);
+        stage_masks(s_masks, wa.masks, wa.n_mats);
         w.smem_masks = s_masks;
     }
     uint32_t x, ly, y;
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(kThreads) secondary_kernel(WorldArgs<World> wa
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
     World w = wa.w;
     if constexpr (std::is_same<World, WorldCompact>::value) {
-        stage_masks(s_masks, wa.masks);
+        stage_masks(s_masks, wa.masks, wa.n_mats);
         w.smem_masks = s_masks;
     }
     uint32_t x, ly, y;
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(kThreads) frame_kernel(WorldArgs<World> wa, co
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
     World w = wa.w;
     if constexpr (std::is_same<World, WorldCompact>::value) {
-        stage_masks(s_masks, wa.masks);
+        stage_masks(s_masks, wa.masks, wa.n_mats);
         w.smem_masks = s_masks;
     }
     uint32_t x, ly, y;
@@ -400,7 +403,7 @@ __global__ void pick_kernel(WorldArgs<World> wa, CamDev cam, ViewDev v, uint8_t 
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
     World w = wa.w;
     if constexpr (std::is_same<World, WorldCompact>::value) {
-        stage_masks(s_masks, wa.masks);
+        stage_masks(s_masks, wa.masks, wa.n_mats);
         w.smem_masks = s_masks;
     }
     const bool lead = threadIdx.x == 0;
@@ -503,7 +506,7 @@ __global__ void count_virtual_kernel(const uint32_t *__restrict__ chunks, const 
     if ((threadIdx.x & 31u) == 0 && m) atomicAdd(counter, (unsigned int)__popc(m));
 }
 
-// chunks2[(cd+1)^3]: bit 31 = far-empty chunk with low byte n_free = 8*(dist-1) - 2; else 0-based brick
+// chunks2[(cd+1)^3]: bit 31 = far-empty chunk with low byte n_free = 8*(dist-1) - 1; else 0-based brick
 // index (real bricks keep the reference numbering, virtual bricks follow).  brick_chunk[b] = linear chunk index.
 __global__ void build_chunks2_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ dist, uint32_t *__restrict__ chunks2,
                                      uint32_t *__restrict__ brick_chunk, int cd, uint32_t n_real, unsigned int *counter) {
@@ -524,7 +527,7 @@ __global__ void build_chunks2_kernel(const uint32_t *__restrict__ chunks, const 
             brick_chunk[e] = (uint32_t)j;
         } else {
             const int r = (int)dist[j] - 1;  // rings of empty in-map chunks around this one (>= 1 here)
-            e = 0x80000000u | (uint32_t)min(max(8 * r - 2, 0), 255);
+            e = 0x80000000u | (uint32_t)min(max(8 * r - 1, 0), 255);
         }
     }
     chunks2[i] = e;
@@ -547,7 +550,7 @@ __global__ void brick_rowmask_kernel(const uint8_t *__restrict__ bricks8, size_t
 // Block-level clearance.  One CTA per brick, one thread per block.  The occupancy of the 5x5x5 chunk
 // neighbourhood is staged in shared memory as 40x40 rows of 40 x-bits (out-of-map = occupied); each
 // empty block searches growing Chebyshev shells for the nearest occupied block, D capped at 16, and
-// stores kMatLimit + max(D - 3, 0).
+// stores kMatLimit + max(D - 2, 0) (see trace_map_fast for the bound).
 constexpr int kClearCap = 16;
 __global__ void __launch_bounds__(512) clearance_kernel(const uint32_t *__restrict__ chunks2, int cd, const uint32_t *__restrict__ brick_chunk,
                                                         const uint8_t *__restrict__ rowmask, uint8_t *__restrict__ bricks8) {
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(512) clearance_kernel(const uint32_t *__restri
         }
         if (found) { D = r; break; }
     }
-    bricks8[addr] = (uint8_t)(kMatLimit + max(D - 3, 0));
+    bricks8[addr] = (uint8_t)(kMatLimit + max(D - 2, 0));
 }
 
 // ---- bandwidth probes (roofline denominators) ----------------------------------

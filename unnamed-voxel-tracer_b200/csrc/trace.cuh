@@ -196,6 +196,86 @@ __device__ __forceinline__ void trace_map(const World &w, float ox, float oy, fl
     out.trips = (uint32_t)trip;
 }
 
+// One DDA step (map.glsl:157-162), hand-scheduled and branch-free: 6 ops for t, 3 compares, min3,
+// 6 ops for within += dir * t[minIdx], then the stepped axis is reset / advanced under its predicate.
+// .rn ops are never contracted.  t[minIdx] is the minimum of the three (ties carry equal values;
+// the fast path has no NaNs), and minIdx follows the reference's strict-less-than cascade.
+// operands: %0-%5 = gx gy gz wx wy wz (read-write); then isx isy isz tgx tgy tgz invx invy invz dx dy dz rsx rsy rsz
+__device__ __forceinline__ void dda_step(int &gx, int &gy, int &gz, float &wx, float &wy, float &wz, int isx, int isy, int isz,
+                                         float tgx, float tgy, float tgz, float invx, float invy, float invz,
+                                         float dx, float dy, float dz, float rsx, float rsy, float rsz) {
+    asm volatile("{\n\t"
+                 ".reg .pred pxy, pmx, pmy, pmz;\n\t"
+                 ".reg .f32 tx, ty, tz, tm, ax, ay, az;\n\t"
+                 "sub.rn.f32 tx, %9, %3;\n\t"
+                 "sub.rn.f32 ty, %10, %4;\n\t"
+                 "sub.rn.f32 tz, %11, %5;\n\t"
+                 "mul.rn.f32 tx, tx, %12;\n\t"
+                 "mul.rn.f32 ty, ty, %13;\n\t"
+                 "mul.rn.f32 tz, tz, %14;\n\t"
+                 "setp.lt.f32 pxy, tx, ty;\n\t"
+                 "setp.lt.and.f32 pmx, tx, tz, pxy;\n\t"
+                 "setp.lt.and.f32 pmy, ty, tz, !pxy;\n\t"
+                 "min.f32 tm, tx, ty;\n\t"
+                 "min.f32 tm, tm, tz;\n\t"
+                 "mul.rn.f32 ax, %15, tm;\n\t"
+                 "mul.rn.f32 ay, %16, tm;\n\t"
+                 "mul.rn.f32 az, %17, tm;\n\t"
+                 "add.rn.f32 %3, %3, ax;\n\t"
+                 "add.rn.f32 %4, %4, ay;\n\t"
+                 "add.rn.f32 %5, %5, az;\n\t"
+                 "or.pred pmz, pmx, pmy;\n\t"
+                 "@pmx mov.f32 %3, %18;\n\t"
+                 "@pmy mov.f32 %4, %19;\n\t"
+                 "@!pmz mov.f32 %5, %20;\n\t"
+                 "@pmx add.s32 %0, %0, %6;\n\t"
+                 "@pmy add.s32 %1, %1, %7;\n\t"
+                 "@!pmz add.s32 %2, %2, %8;\n\t"
+                 "}"
+                 : "+r"(gx), "+r"(gy), "+r"(gz), "+f"(wx), "+f"(wy), "+f"(wz)
+                 : "r"(isx), "r"(isy), "r"(isz), "f"(tgx), "f"(tgy), "f"(tgz), "f"(invx), "f"(invy), "f"(invz),
+                   "f"(dx), "f"(dy), "f"(dz), "f"(rsx), "f"(rsy), "f"(rsz));
+}
+
+// same step; additionally %6 %7 = (minIdx == 0), (minIdx == 1)
+__device__ __forceinline__ void dda_step_last(int &gx, int &gy, int &gz, float &wx, float &wy, float &wz, int &mxi, int &myi,
+                                              int isx, int isy, int isz, float tgx, float tgy, float tgz, float invx, float invy, float invz,
+                                              float dx, float dy, float dz, float rsx, float rsy, float rsz) {
+    asm volatile("{\n\t"
+                 ".reg .pred pxy, pmx, pmy, pmz;\n\t"
+                 ".reg .f32 tx, ty, tz, tm, ax, ay, az;\n\t"
+                 "sub.rn.f32 tx, %11, %3;\n\t"
+                 "sub.rn.f32 ty, %12, %4;\n\t"
+                 "sub.rn.f32 tz, %13, %5;\n\t"
+                 "mul.rn.f32 tx, tx, %14;\n\t"
+                 "mul.rn.f32 ty, ty, %15;\n\t"
+                 "mul.rn.f32 tz, tz, %16;\n\t"
+                 "setp.lt.f32 pxy, tx, ty;\n\t"
+                 "setp.lt.and.f32 pmx, tx, tz, pxy;\n\t"
+                 "setp.lt.and.f32 pmy, ty, tz, !pxy;\n\t"
+                 "min.f32 tm, tx, ty;\n\t"
+                 "min.f32 tm, tm, tz;\n\t"
+                 "mul.rn.f32 ax, %17, tm;\n\t"
+                 "mul.rn.f32 ay, %18, tm;\n\t"
+                 "mul.rn.f32 az, %19, tm;\n\t"
+                 "add.rn.f32 %3, %3, ax;\n\t"
+                 "add.rn.f32 %4, %4, ay;\n\t"
+                 "add.rn.f32 %5, %5, az;\n\t"
+                 "or.pred pmz, pmx, pmy;\n\t"
+                 "@pmx mov.f32 %3, %20;\n\t"
+                 "@pmy mov.f32 %4, %21;\n\t"
+                 "@!pmz mov.f32 %5, %22;\n\t"
+                 "@pmx add.s32 %0, %0, %8;\n\t"
+                 "@pmy add.s32 %1, %1, %9;\n\t"
+                 "@!pmz add.s32 %2, %2, %10;\n\t"
+                 "selp.s32 %6, 1, 0, pmx;\n\t"
+                 "selp.s32 %7, 1, 0, pmy;\n\t"
+                 "}"
+                 : "+r"(gx), "+r"(gy), "+r"(gz), "+f"(wx), "+f"(wy), "+f"(wz), "=r"(mxi), "=r"(myi)
+                 : "r"(isx), "r"(isy), "r"(isz), "f"(tgx), "f"(tgy), "f"(tgz), "f"(invx), "f"(invy), "f"(invz),
+                   "f"(dx), "f"(dy), "f"(dz), "f"(rsx), "f"(rsy), "f"(rsz));
+}
+
 // ---- traceMap, B200 fast path ----------------------------------------------------------
 // Same trips, same arithmetic as trace_map (map.glsl:83-168); what changes is what is FETCHED
 // and how the loop is laid out:
@@ -208,25 +288,28 @@ __device__ __forceinline__ void trace_map(const World &w, float ox, float oy, fl
 //    bounds test, no `pos`, no loads.  Proof: at 8-sub-voxel steps g moves exactly one block along
 //    one axis per trip and `pos` is in g's block or, when a `within` component rounds up to 8, one
 //    block further; with D the Chebyshev distance (blocks) from the looked-up block to the nearest
-//    non-empty block or map face, trips j <= D - 3 look up blocks within j + 2 < D of it.  The
-//    chunk-level field gives D >= 8R + 1 for R empty chunk rings, hence n_free = 8R - 2 there;
-//    the block-level field (clearance kernel) gives n_free = min(D, 8) - 3 inside bricks.
-//    (COUNT instantiations ignore n_free so that the reference counters stay exact.)
-//  * at block steps with within < 8 the block holding `pos` is g >> 3, so the float->int
-//    conversions of map.glsl:108 are skipped until a non-empty block is found.
+//    non-empty block or map face: with c_j in {0,1}^3 the round-up carry of trip j, the block looked
+//    up at trip j is P_0 - c_0 + (j unit steps) + c_j, within j + 1 of P_0, so trips j <= D - 2 are
+//    free.  The chunk-level field gives D >= 8R + 1 for R empty chunk rings, hence n_free = 8R - 1
+//    there; the block-level field (clearance_kernel) gives n_free = min(D, 16) - 2 inside bricks.
+//    (COUNT == 1 ignores n_free so that the reference counters stay exact.)
+//  * WARP LOCKSTEP.  All 32 lanes are at the same trip index.  After a round of lookups every live
+//    lane knows how many of its next trips are free; the warp runs the minimum of those as a
+//    divergence-free, branch-free DDA loop with a uniform trip count, then the lanes whose free
+//    trips ran out look up again.  Lanes whose ray has ended keep executing the arithmetic on dead
+//    state (no memory traffic) and are parked with limit = kDead.
 //  * the guard layer of chunks2 (index cd on any axis) removes the chunk-range test: `pos` can
 //    exceed the map by at most one block on the high side while g is in bounds.
 //  * sub-voxel occupancy is a bit test in shared memory; colour and block word are fetched once,
 //    at the hit.  Per-phase constants (target face, reset value, signed step per axis) live in
 //    registers and are rewritten only when the step size changes.
-//  * the loop is rotated (DDA step first, then the next trip's lookup) so that the min-axis
-//    predicates are still live when a hit needs them for the face id.
 //
 // Rays with non-finite reciprocals or origins beyond 2^20 sub-voxels take the generic path,
 // whose corner-case behaviour (NaN ordering, saturation) is the specification.
 constexpr uint32_t kMatLimit = 224;  // brick bytes >= kMatLimit encode empty blocks
+constexpr int kDead = 0x40000000;    // `limit` of a lane without a live ray
 
-// Must be called by ALL 32 lanes of a warp (it uses full-mask warp votes); `active` = this lane has a ray.
+// Must be called by ALL 32 lanes of a warp (it uses full-mask warp reductions); `active` = this lane has a ray.
 template <int COUNT>
 __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool active, float ox, float oy, float oz, float dx, float dy, float dz,
                                                int max_steps, int bound, Hit &out, TripCounts &tc) {
@@ -267,121 +350,93 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
     }
 
     const uint32_t cd1 = w.cd1;
-    int trip = 0;   // warp-uniform
-    int limit = 0;  // trips in [trip, limit) need no lookup
+    int trip = 0;                     // warp-uniform
+    int limit = fast ? 0 : kDead;     // trips in [trip, limit) need no lookup; kDead parks the lane
+    bool mx = true, my = false;       // minIdx of the previous trip == 0 / == 1 (starts at 0, map.glsl:98)
 
-    // Everything a trip does before its DDA step (map.glsl:107-144).  lastx/lasty: minIdx of the
-    // previous trip was 0 / 1.  Returns false when the ray ends here.
-    auto visit = [&](bool lastx, bool lasty) -> bool {
-        if ((unsigned)gx >= (unsigned)bound || (unsigned)gy >= (unsigned)bound || (unsigned)gz >= (unsigned)bound) {
-            out.exit_kind = 2;
-            out.trips = (uint32_t)trip;
-            return false;
-        }
-        if (COUNT == 2) tc.t_in++;  // lookups performed
-        uint32_t px = (uint32_t)gx, py = (uint32_t)gy, pz = (uint32_t)gz;
-        // at block steps g is a multiple of 8; with within < 8 the block of `pos` is g >> 3
-        const bool lazy = big && fmaxf(fmaxf(wx, wy), wz) < 8.0f;
-        if (!lazy) {
-            px += __float2uint_rz(wx);
-            py += __float2uint_rz(wy);
-            pz += __float2uint_rz(wz);
-        }
-        const uint32_t e = __ldg(&w.chunks2[(px >> 6) + cd1 * ((py >> 6) + (pz >> 6) * cd1)]);
-        uint32_t mat = 0;
-        int n_free;
-        if ((int)e < 0) {
-            n_free = (int)(e & 0xFFu);
-        } else {
-            if (COUNT == 1 && e < w.n_real_bricks) tc.t_chunk++;
-            const uint32_t b = __ldg(&w.bricks8[e * 512u + (((px >> 3) & 7u) | (py & 0x38u) | ((pz & 0x38u) << 3))]);
-            n_free = (int)b - (int)kMatLimit;
-            if (n_free < 0) { mat = b; n_free = 0; }
-        }
-        if (COUNT == 1) n_free = 0;  // exact reference counters need every trip's lookup
-        limit = trip + 1 + n_free;
-        if (mat != 0) {
-            if (COUNT == 1) tc.t_block++;
-            if (lazy) {
-                px += __float2uint_rz(wx);
-                py += __float2uint_rz(wy);
-                pz += __float2uint_rz(wz);
-            }
-            const uint32_t bit = (px & 7u) | ((py & 7u) << 3) | ((pz & 7u) << 6);
-            const uint32_t word = w.smem_masks[mat * 16u + (bit >> 5)];
-            if ((word >> (bit & 31u)) & 1u) {
-                out.data = __ldg(&w.mat_color[mat * 512u + bit]);
-                out.face = lastx ? (posx ? 1u : 2u) : (lasty ? (posy ? 3u : 4u) : (posz ? 5u : 6u));
-                out.hx = (float)gx + wx;
-                out.hy = (float)gy + wy;
-                out.hz = (float)gz + wz;
-                out.px = px; out.py = py; out.pz = pz;
-                out.block = __ldg(&w.mat_word[mat]);
-                out.exit_kind = 0;
-                out.trips = (uint32_t)trip + 1u;
-                return false;
-            }
-            if (big) {  // drop to sub-voxel steps (map.glsl:131-135)
-                gx += __float2int_rz(wx);
-                gy += __float2int_rz(wy);
-                gz += __float2int_rz(wz);
-                wx = wx - floorf(wx);
-                wy = wy - floorf(wy);
-                wz = wz - floorf(wz);
-                big = false;
-                tgx = posx ? 1.0f : 0.0f; tgy = posy ? 1.0f : 0.0f; tgz = posz ? 1.0f : 0.0f;
-                rsx = posx ? 0.0f : 0.999f; rsy = posy ? 0.0f : 0.999f; rsz = posz ? 0.0f : 0.999f;
-                isx = posx ? 1 : -1; isy = posy ? 1 : -1; isz = posz ? 1 : -1;
-            }
-        } else if (!big) {  // rise to block steps (map.glsl:140-144)
-            wx += (float)(gx & 7);
-            wy += (float)(gy & 7);
-            wz += (float)(gz & 7);
-            gx &= ~7;
-            gy &= ~7;
-            gz &= ~7;
-            big = true;
-            tgx = posx ? 8.0f : 0.0f; tgy = posy ? 8.0f : 0.0f; tgz = posz ? 8.0f : 0.0f;
-            rsx = posx ? 0.0f : 8.0f * 0.999f; rsy = posy ? 0.0f : 8.0f * 0.999f; rsz = posz ? 0.0f : 8.0f * 0.999f;
-            isx = posx ? 8 : -8; isy = posy ? 8 : -8; isz = posz ? 8 : -8;
-        }
-        return true;
-    };
-
-    // Warp-lockstep schedule: all lanes of the warp are at the same trip index.  After a round of
-    // lookups every live lane knows how many of its next trips are free; the warp runs the minimum
-    // of those as a divergence-free DDA loop (uniform trip count), then looks up again together.
-    // Lanes whose ray has ended keep executing the arithmetic on dead state (no memory traffic).
-    bool alive = fast;
-    if (alive) alive = visit(true, false);  // trip 0: minIdx starts at 0 (map.glsl:98)
-    bool mx = true, my = false;
     for (;;) {
-        const unsigned live = __ballot_sync(0xFFFFFFFFu, alive);
-        if (live == 0u) break;
-        int k = __reduce_min_sync(0xFFFFFFFFu, alive ? limit - trip : 0x7FFFFFFF);
-        k = min(k, max_steps - trip);  // max_steps > 0 on every live lane
-        for (int j = 0; j < k; ++j) {
-            // dda stepping (map.glsl:157-162)
-            const float tx = (tgx - wx) * invx;
-            const float ty = (tgy - wy) * invy;
-            const float tz = (tgz - wz) * invz;
-            const bool xy = tx < ty;
-            mx = xy && (tx < tz);
-            my = !xy && (ty < tz);
-            const float tm = mx ? tx : (my ? ty : tz);
-            wx += dx * tm;
-            wy += dy * tm;
-            wz += dz * tm;
-            if (mx) { gx += isx; wx = rsx; }
-            else if (my) { gy += isy; wy = rsy; }
-            else { gz += isz; wz = rsz; }
+        // ---- lookups for the lanes whose free trips ran out (map.glsl:107-144) ------------
+        if (trip >= limit) {
+            if ((unsigned)gx >= (unsigned)bound || (unsigned)gy >= (unsigned)bound || (unsigned)gz >= (unsigned)bound) {
+                out.exit_kind = 2;
+                out.trips = (uint32_t)trip;
+                limit = kDead;
+            } else {
+                if (COUNT == 2) tc.t_in++;  // lookups performed
+                const uint32_t px = (uint32_t)gx + __float2uint_rz(wx);
+                const uint32_t py = (uint32_t)gy + __float2uint_rz(wy);
+                const uint32_t pz = (uint32_t)gz + __float2uint_rz(wz);
+                const uint32_t e = __ldg(&w.chunks2[(px >> 6) + cd1 * ((py >> 6) + (pz >> 6) * cd1)]);
+                int code;  // brick byte semantics: < kMatLimit material, else kMatLimit + n_free
+                if ((int)e < 0) {
+                    code = (int)(e & 0xFFu) + (int)kMatLimit;
+                } else {
+                    if (COUNT == 1 && e < w.n_real_bricks) tc.t_chunk++;
+                    code = (int)__ldg(&w.bricks8[e * 512u + (((px >> 3) & 7u) | (py & 0x38u) | ((pz & 0x38u) << 3))]);
+                }
+                const int n_free = (COUNT == 1) ? 0 : max(code - (int)kMatLimit, 0);  // exact counters need every lookup
+                limit = trip + 1 + n_free;
+                if (code < (int)kMatLimit && code != 0) {  // a block: test the sub-voxel
+                    const uint32_t mat = (uint32_t)code;
+                    if (COUNT == 1) tc.t_block++;
+                    const uint32_t bit = (px & 7u) | ((py & 7u) << 3) | ((pz & 7u) << 6);
+                    const uint32_t word = w.smem_masks[mat * 16u + (bit >> 5)];
+                    if ((word >> (bit & 31u)) & 1u) {
+                        out.data = __ldg(&w.mat_color[mat * 512u + bit]);
+                        out.face = mx ? (posx ? 1u : 2u) : (my ? (posy ? 3u : 4u) : (posz ? 5u : 6u));
+                        out.hx = (float)gx + wx;
+                        out.hy = (float)gy + wy;
+                        out.hz = (float)gz + wz;
+                        out.px = px; out.py = py; out.pz = pz;
+                        out.block = __ldg(&w.mat_word[mat]);
+                        out.exit_kind = 0;
+                        out.trips = (uint32_t)trip + 1u;
+                        limit = kDead;
+                    } else if (big) {  // drop to sub-voxel steps (map.glsl:131-135)
+                        gx += __float2int_rz(wx);
+                        gy += __float2int_rz(wy);
+                        gz += __float2int_rz(wz);
+                        wx = wx - floorf(wx);
+                        wy = wy - floorf(wy);
+                        wz = wz - floorf(wz);
+                        big = false;
+                        tgx = posx ? 1.0f : 0.0f; tgy = posy ? 1.0f : 0.0f; tgz = posz ? 1.0f : 0.0f;
+                        rsx = posx ? 0.0f : 0.999f; rsy = posy ? 0.0f : 0.999f; rsz = posz ? 0.0f : 0.999f;
+                        isx = posx ? 1 : -1; isy = posy ? 1 : -1; isz = posz ? 1 : -1;
+                    }
+                } else if (!big) {  // rise to block steps (map.glsl:140-144)
+                    wx += (float)(gx & 7);
+                    wy += (float)(gy & 7);
+                    wz += (float)(gz & 7);
+                    gx &= ~7;
+                    gy &= ~7;
+                    gz &= ~7;
+                    big = true;
+                    tgx = posx ? 8.0f : 0.0f; tgy = posy ? 8.0f : 0.0f; tgz = posz ? 8.0f : 0.0f;
+                    rsx = posx ? 0.0f : 8.0f * 0.999f; rsy = posy ? 0.0f : 8.0f * 0.999f; rsz = posz ? 0.0f : 8.0f * 0.999f;
+                    isx = posx ? 8 : -8; isy = posy ? 8 : -8; isz = posz ? 8 : -8;
+                }
+            }
+        }
+
+        // ---- how many trips can the whole warp run without a lookup? ----------------------
+        int k = __reduce_min_sync(0xFFFFFFFFu, limit - trip);
+        if (k >= kDead / 2) break;             // no live lane left
+        k = min(k, max_steps - trip);          // max_steps > 0 on every live lane
+
+        // ---- k DDA steps, branch-free (map.glsl:157-162) -----------------------------------
+        for (int j = 1; j < k; ++j) dda_step(gx, gy, gz, wx, wy, wz, isx, isy, isz, tgx, tgy, tgz, invx, invy, invz, dx, dy, dz, rsx, rsy, rsz);
+        {   // the last step of the run also reports minIdx: a hit in the next lookup needs it for the face id
+            int mxi, myi;
+            dda_step_last(gx, gy, gz, wx, wy, wz, mxi, myi, isx, isy, isz, tgx, tgy, tgz, invx, invy, invz, dx, dy, dz, rsx, rsy, rsz);
+            mx = mxi != 0;
+            my = myi != 0;
         }
         trip += k;
         if (trip >= max_steps) {  // iteration cap: miss (map.glsl:167)
-            if (alive) out.trips = (uint32_t)trip;
+            if (limit < kDead) out.trips = (uint32_t)trip;
             break;
         }
-        if (alive) alive = visit(mx, my);
     }
     if (COUNT == 1 && fast) tc.t_in = out.trips;  // every executed trip passed the bounds test
 }

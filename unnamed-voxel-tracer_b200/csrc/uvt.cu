@@ -229,6 +229,7 @@ WorldArgs<WorldRef> world_ref(const uvt_ctx *c) {
     a.w.cd = c->cd;
     a.w.n_slots = c->n_slots;
     a.masks = nullptr;
+    a.n_mats = 0;
     return a;
 }
 
@@ -244,6 +245,7 @@ WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     a.w.smem_masks = nullptr;
     a.w.cd = c->cd;
     a.masks = c->d_mat_mask;
+    a.n_mats = (uint32_t)(c->mat_words.size() - 1);
     return a;
 }
 

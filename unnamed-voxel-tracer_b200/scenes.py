@@ -31,10 +31,10 @@ def camera_k0(dim=512):
 
 
 def camera_k1(dim=512):
-    """pitched/yawed view over the hills (trees + shadows in view)."""
-    s = dim / 512.0
-    base = max(procgen.height(dim, int(200 * s), int(140 * s)), 16)
-    return camera((200.0 * s, float(base + 28), 140.0 * s), pitch_yaw(0.35, 0.6))
+    """pitched/yawed view over the hills (trees + shadows in view).  The same block coordinates for every world
+    size: procgen only plants trees for x, z < 500 (procgen.zig:47), so the W4 camera stays in that corner."""
+    base = max(procgen.height(dim, 200, 140), 16)
+    return camera((200.0, float(base + 28), 140.0), pitch_yaw(0.35, 0.6))
 
 
 def sweep_poses(dim, n=256, seed=LCG_SEED):

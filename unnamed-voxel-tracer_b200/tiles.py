@@ -55,6 +55,8 @@ def gather_bands(local, dst=0, group=None):
     """Gather every rank's [rows_per_part, W] band buffer to `dst`; returns [n_parts, rows_per_part, W] there, None elsewhere."""
     import torch
     import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return local.unsqueeze(0)  # single process: nothing to gather
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if world == 1:
         return local.unsqueeze(0)
