@@ -139,6 +139,7 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread
     uvt = importlib.import_module("unnamed-voxel-tracer_b200")
     dim, W, H, shadows, desc = WORKLOADS[args.workload]
     if args.workload in ("c3", "c4", "c5"):
@@ -372,6 +373,7 @@ def run_ours(args):
 def cpu_baseline(uvt, args, dim, W, H, shadows, cam):
     """The oracle (CPU port of the reference GLSL) on this box's host cores: bounded sample of the same workload."""
     import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)
     scale = 1 if W * H <= 1920 * 1080 and dim <= 512 else 4
     Ws, Hs = W // scale, H // scale
     bm = uvt.voxel.VoxelBrickmap.init(dim)
