@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--layout", default="compact", choices=["compact", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed steps (reported in config)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="c4 only: p2p = kernels store finished bands straight into rank 0's frame over NVLink (CUDA IPC peer mapping); "
+                         "nccl = band buffers gathered with NCCL send/recv + reassembly kernel")
     return ap.parse_args()
 
 
@@ -224,10 +227,24 @@ def run_ours(args):
 
     rpp = uvt.tiles.rows_per_part(H, band, world) if tiled else H
     gather_buf = None
+    p2p = tiled and args.gather == "p2p"
+    shared_ptr = None
     if tiled:
         gather_buf = torch.zeros((rpp, W), dtype=torch.int32, device=f"cuda:{local_rank}")
-        ctx.bind_frame_target(gather_buf.data_ptr(), global_rows=False)
         full_frame = torch.empty((H, W), dtype=torch.int32, device=f"cuda:{local_rank}") if rank == 0 else None
+        if p2p:
+            # the presenting rank owns the frame; every rank's kernels store their bands straight into it
+            box = [None]
+            if rank == 0:
+                shared_ptr, handle = ctx.shared_frame_create()
+                box[0] = handle
+            if use_dist:
+                dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                shared_ptr = ctx.shared_frame_open(box[0])
+            ctx.bind_frame_target(shared_ptr, global_rows=True)
+        else:
+            ctx.bind_frame_target(gather_buf.data_ptr(), global_rows=False)
 
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
     pinned = ctx.pinned_empty(W * ctx.local_rows() * 4, np.uint32)
@@ -273,7 +290,7 @@ def run_ours(args):
 
     for i in range(args.warmup):
         device_step(i)
-        if tiled:
+        if tiled and not p2p:
             gather_step()
     barrier()
 
@@ -290,7 +307,7 @@ def run_ours(args):
                 flush.fill_(i & 0xFF)  # evict L2 between timed iterations (untimed)
         ms = device_step(i)
         kernel_ms.append(ms)
-        if tiled:
+        if tiled and not p2p:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             gather_step()
@@ -301,6 +318,20 @@ def run_ours(args):
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop()
+
+    verified = None
+    if p2p:
+        # the peer-stored frame must equal the NCCL-gathered one (checked outside the timed region)
+        host_p2p = np.empty((H, W), np.uint32)
+        if rank == 0:
+            ctx.read_device(shared_ptr, host_p2p)
+        ctx.bind_frame_target(gather_buf.data_ptr(), global_rows=False)
+        device_step(0)
+        gather_step()
+        barrier()
+        if rank == 0:
+            verified = bool(np.array_equal(full_frame.cpu().numpy().view(np.uint32), host_p2p))
+        ctx.bind_frame_target(shared_ptr, global_rows=True)
 
     step_ms_local = float(np.sum(kernel_ms) + np.sum(gather_ms))
     t = torch.tensor([step_ms_local], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -315,22 +346,39 @@ def run_ours(args):
     # ---- e2e: the same metric through the C ABI with host buffers (camera H2D + result D2H inside the timed region)
     cam_host = np.array(cam)
     out_kind = "frame" if shadows else "albedo"
-    for i in range(2):
-        ctx.set_camera(cam_host)
+    full_pinned = ctx.pinned_empty(W * H * 4, np.uint32) if (tiled and rank == 0) else None
+
+    def e2e_step(i):
+        ctx.set_camera(my_poses[i % len(my_poses)] if sweep else cam_host)
         (ctx.dispatch_frame if shadows else ctx.dispatch_primary)()
-        ctx.readback_into(out_kind, pinned)
+        if not tiled:
+            ctx.readback_into(out_kind, pinned)   # synchronous D2H into pinned host memory
+            return
+        # tiled frame: the step's result is the assembled frame on the presenting rank
+        if p2p:
+            ctx.sync()
+            if use_dist:
+                dist.barrier()
+            if rank == 0:
+                ctx.read_device(shared_ptr, full_pinned)
+        else:
+            gather_step()
+            if rank == 0:
+                ctx.read_device(full_frame.data_ptr(), full_pinned)
+
+    for i in range(2):
+        e2e_step(i)
     barrier()
     e0 = time.perf_counter()
     for i in range(args.steps):
-        ctx.set_camera(my_poses[i % len(my_poses)] if sweep else cam_host)
-        (ctx.dispatch_frame if shadows else ctx.dispatch_primary)()
-        ctx.readback_into(out_kind, pinned)   # synchronous D2H into pinned host memory
+        e2e_step(i)
     barrier()
     e2e_s = time.perf_counter() - e0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
     if use_dist:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = rays_all * args.steps / float(te.item()) / 1e9
+    d2h_bytes = W * H * 4 if tiled else int(pinned.nbytes)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -346,8 +394,9 @@ def run_ours(args):
                                       ("poses sharded over %d ranks" % world if sweep else "one independent frame per rank per step, world replicated, no collective"),
                        "l2": "not flushed" if args.no_flush else "flushed between timed steps by a 256 MiB fill (untimed)",
                        "timing": "CUDA events on the launch stream per step, summed; max over ranks", "world_build_s": round(build_s, 2)},
-            "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": 96, "d2h_bytes_per_step": int(pinned.nbytes),
-                    "what": "uvt_set_camera + dispatch + uvt_readback of the RGBA8 %s into pinned host memory, wall clock" % out_kind},
+            "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": 96, "d2h_bytes_per_step": d2h_bytes,
+                    "what": ("uvt_set_camera + dispatch + (band exchange) + D2H of the assembled RGBA8 frame on rank 0 into pinned host memory, wall clock" if tiled
+                             else "uvt_set_camera + dispatch + uvt_readback of the RGBA8 %s into pinned host memory, wall clock" % out_kind)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
@@ -361,10 +410,17 @@ def run_ours(args):
             "wall_ms_per_step": wall / args.steps * 1e3,
         }
         if tiled:
-            line["gather_ms"] = float(np.mean(gather_ms))
+            line["gather_ms"] = float(np.mean(gather_ms)) if gather_ms else 0.0
+            line["config"]["gather"] = ("p2p: kernels store bands into rank 0's frame over NVLink (CUDA IPC peer mapping), no collective"
+                                        if p2p else "nccl: torch.distributed.gather of band buffers + reassembly kernel")
+            if verified is not None:
+                line["config"]["p2p_frame_equals_nccl_gather"] = verified
         if args.gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(uvt, args, dim, W, H, shadows, cam)
         print(json.dumps(line))
+    if p2p and rank != 0:
+        ctx.bind_frame_target(0, global_rows=False)
+        ctx.shared_frame_close(shared_ptr)
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -184,6 +184,15 @@ int  uvt_device_ptr(uvt_ctx *ctx, uvt_buffer_kind kind, void **dptr);
 /* Redirect the FRAME output to caller-owned device memory (may be a peer-mapped
  * pointer of another GPU: finished bands are then stored straight over NVLink). */
 int  uvt_bind_frame_target(uvt_ctx *ctx, void *dptr, uint32_t reserved, uint32_t global_rows);
+/* Peer-to-peer frame (the fused alternative to the gather): the presenting rank creates a full WxH RGBA8 frame
+ * and exports a CUDA IPC handle (64 bytes); every other rank opens it and binds the mapped pointer with
+ * uvt_bind_frame_target(ptr, 0, 1): its kernels then store finished pixels straight into the presenting
+ * GPU's memory over NVLink, so no gather and no reassembly pass remain. */
+int  uvt_shared_frame_create(uvt_ctx *ctx, void **dptr, unsigned char handle_out[64]);
+int  uvt_shared_frame_open(uvt_ctx *ctx, const unsigned char handle[64], void **dptr);
+int  uvt_shared_frame_close(uvt_ctx *ctx, void *dptr);
+/* Copy `bytes` from any device pointer visible to this ctx (e.g. the shared frame) to host memory. */
+int  uvt_read_device(uvt_ctx *ctx, const void *dptr, void *dst, size_t bytes);
 /* Rank 0 after the NCCL gather: `gathered` holds n_parts compact band buffers of rows_per_part rows
  * back to back; writes the assembled WxH frame (one kernel on the ctx stream). */
 int  uvt_deinterleave(uvt_ctx *ctx, const void *gathered, void *frame, uint32_t rows_per_part);

@@ -82,6 +82,10 @@ SIGNATURES = {
     "uvt_device_ptr": (c_int, [c_p, c_int, P(c_p)]),
     "uvt_bind_frame_target": (c_int, [c_p, c_p, c_u32, c_u32]),
     "uvt_deinterleave": (c_int, [c_p, c_p, c_p, c_u32]),
+    "uvt_shared_frame_create": (c_int, [c_p, P(c_p), c_p]),
+    "uvt_shared_frame_open": (c_int, [c_p, c_p, P(c_p)]),
+    "uvt_shared_frame_close": (c_int, [c_p, c_p]),
+    "uvt_read_device": (c_int, [c_p, c_p, c_p, c_size]),
     "uvt_alloc_pinned": (c_int, [c_p, c_size, P(c_p)]),
     "uvt_free_pinned": (c_int, [c_p, c_p]),
     "uvt_count_pass": (c_int, [c_p, c_int, P(Counters)]),

@@ -81,6 +81,7 @@ struct uvt_ctx {
     size_t gbuf_pixels = 0;  // allocated pixels (all layers)
     uint32_t *frame_target = nullptr;
     bool frame_target_global_rows = false;
+    void *shared_frame = nullptr;  // owned full-frame allocation exported over CUDA IPC (presenting rank)
 
     // ---- counters / timing
     DevCounters *d_counters = nullptr;
@@ -492,7 +493,7 @@ void uvt_destroy(uvt_ctx *c) {
     cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
     cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
-    cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink);
+    cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame);
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 2; ++j)
             if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
@@ -856,6 +857,45 @@ int uvt_bind_frame_target(uvt_ctx *c, void *dptr, uint32_t row_offset_rows, uint
     (void)row_offset_rows;
     c->frame_target = (uint32_t *)dptr;
     c->frame_target_global_rows = global_rows != 0;
+    return UVT_OK;
+}
+
+int uvt_shared_frame_create(uvt_ctx *c, void **dptr, unsigned char handle_out[64]) {
+    if (!c || !dptr || !handle_out) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, c->W && c->H, "no G-buffer (uvt_resize first)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->shared_frame);
+    c->shared_frame = nullptr;
+    UVT_CUDA(c, cudaMalloc(&c->shared_frame, (size_t)c->W * c->H * 4));
+    UVT_CUDA(c, cudaMemset(c->shared_frame, 0, (size_t)c->W * c->H * 4));
+    cudaIpcMemHandle_t h;
+    UVT_CUDA(c, cudaIpcGetMemHandle(&h, c->shared_frame));
+    std::memcpy(handle_out, &h, 64);
+    *dptr = c->shared_frame;
+    return UVT_OK;
+}
+
+int uvt_shared_frame_open(uvt_ctx *c, const unsigned char handle[64], void **dptr) {
+    if (!c || !dptr || !handle) return UVT_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    UVT_CUDA(c, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return UVT_OK;
+}
+
+int uvt_shared_frame_close(uvt_ctx *c, void *dptr) {
+    if (!c || !dptr) return UVT_ERR_INVALID;
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->frame_target == dptr) c->frame_target = nullptr;
+    UVT_CUDA(c, cudaIpcCloseMemHandle(dptr));
+    return UVT_OK;
+}
+
+int uvt_read_device(uvt_ctx *c, const void *dptr, void *dst, size_t bytes) {
+    if (!c || !dptr || !dst) return UVT_ERR_INVALID;
+    UVT_CUDA(c, cudaMemcpyAsync(dst, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     return UVT_OK;
 }
 

@@ -147,6 +147,27 @@ class Context:
     def deinterleave(self, gathered_ptr, frame_ptr, rows_per_part):
         self.check(self.L.uvt_deinterleave(self.handle, ctypes.c_void_p(gathered_ptr), ctypes.c_void_p(frame_ptr), rows_per_part))
 
+    def shared_frame_create(self):
+        """Presenting rank: allocate the full WxH frame and return (device pointer, 64-byte CUDA IPC handle)."""
+        p = ctypes.c_void_p()
+        h = (ctypes.c_ubyte * 64)()
+        self.check(self.L.uvt_shared_frame_create(self.handle, ctypes.byref(p), h))
+        return p.value, bytes(h)
+
+    def shared_frame_open(self, handle):
+        """Other ranks: map the presenting rank's frame into this process (peer access over NVLink)."""
+        p = ctypes.c_void_p()
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        self.check(self.L.uvt_shared_frame_open(self.handle, buf, ctypes.byref(p)))
+        return p.value
+
+    def shared_frame_close(self, dptr):
+        self.check(self.L.uvt_shared_frame_close(self.handle, ctypes.c_void_p(dptr)))
+
+    def read_device(self, dptr, out):
+        self.check(self.L.uvt_read_device(self.handle, ctypes.c_void_p(dptr), out.ctypes.data, out.nbytes))
+        return out
+
     _KINDS = {"albedo": (N.UVT_BUF_ALBEDO, np.uint32, ()), "normal": (N.UVT_BUF_NORMAL, np.uint32, ()),
               "position": (N.UVT_BUF_POSITION, np.float32, (4,)), "illumination": (N.UVT_BUF_ILLUMINATION, np.uint32, ()),
               "frame": (N.UVT_BUF_FRAME, np.uint32, ()), "hit": (N.UVT_BUF_HIT, N.HIT_DTYPE, ())}
