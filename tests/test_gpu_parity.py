@@ -356,3 +356,71 @@ def test_full_size_layouts_agree_and_rows_match_oracle(uvt, oracle, w1, size):
         assert np.array_equal(a["illumination"], r["illumination"])
         assert channel_diff(a["frame"], r["frame"]).max() <= 1
         assert ca == r["primary_counters"]
+
+
+# ---- W4 (procgen 2048) and the sealed-ray / free-trip machinery ----------------------------------------
+@pytest.fixture(scope="module")
+def w4(uvt, scene_factory):
+    ctx = uvt.Context(0, hit_buffer=True, map_dim=2048)
+    sc = scene_factory(2048, "procgen", ctx=ctx)
+    yield ctx, sc
+    ctx.close()
+
+
+def test_w4_world_parity(uvt, oracle, w4):
+    """BASELINE config 3 world (procgen 2048, trees in the x,z<500 corner) at a size the oracle finishes in seconds."""
+    ctx, sc = w4
+    assert ctx.effective_layout() == "compact"
+    prm = oracle.params(2048)
+    for cam in (uvt.scenes.camera_k1(2048), uvt.scenes.camera_k0(2048)):
+        ctx.resize(384, 216)
+        g = gpu_render(ctx, cam)
+        r = oracle.render(sc.oracle_world, cam, 384, 216, prm)
+        assert_primary_parity(g, r)
+        assert np.array_equal(g["illumination"], r["illumination"])
+        assert channel_diff(g["frame"], r["frame"]).max() <= 1
+        assert ctx.count_pass("primary") == r["primary_counters"]
+    # a few poses of the C5 sweep
+    ctx.resize(160, 90)
+    for cam in uvt.scenes.sweep_poses(2048, 6):
+        g = gpu_render(ctx, cam)
+        assert_primary_parity(g, oracle.render(sc.oracle_world, cam, 160, 90, prm))
+
+
+def test_sealed_rays_and_map_faces(uvt, oracle, w1):
+    """Rays that climb above every occupied block are retired early (sealed) — results must still equal the
+    192-trip march; cameras near a map face must NOT seal (the ray may leave the map first)."""
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    ctx.resize(160, 90)
+    up = np.array([[1, 0, 0, 0], [0, 0, -1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], np.float32)  # looking straight up
+    cams = [oracle.make_camera((256.0, 30.0, 256.0), up),                                     # sealed almost at once
+            oracle.make_camera((256.0, 200.0, 256.0), pitch_yaw_matrix(uvt, -0.5, 1.0)),      # high, looking up
+            oracle.make_camera((256.0, 500.0, 256.0), up),                                     # leaves through the top face
+            oracle.make_camera((8.0, 60.0, 8.0), pitch_yaw_matrix(uvt, -0.3, 3.9)),           # corner, looking out and up
+            oracle.make_camera((500.0, 40.0, 256.0), pitch_yaw_matrix(uvt, -0.2, np.pi / 2)),  # near +x face, looking out
+            oracle.make_camera((256.0, 25.0, 256.0), pitch_yaw_matrix(uvt, -0.9, 0.3))]
+    for cam in cams:
+        g = gpu_render(ctx, cam)
+        r = oracle.render(sc.oracle_world, cam, 160, 90)
+        assert_primary_parity(g, r)
+        assert np.array_equal(g["illumination"], r["illumination"])
+    # odd step caps: sealing and the lockstep cap must follow maxSteps
+    for cap in (1, 7, 64, 500):
+        ctx.set_max_steps(cap, 48)
+        g = gpu_render(ctx, camera_k1(uvt, oracle))
+        r = oracle.render(sc.oracle_world, camera_k1(uvt, oracle), 160, 90, oracle.params(512, primary_max_steps=cap))
+        assert_primary_parity(g, r)
+    ctx.set_max_steps(192, 48)
+
+
+def test_fast_path_fetches_fewer_trips(uvt, oracle, w1):
+    """The B200 layout must actually skip fetches: lookups performed < trips executed (and counters stay exact)."""
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    ctx.resize(320, 180)
+    ctx.set_camera(camera_k0(oracle))
+    exact = ctx.count_pass("primary")
+    stats = ctx.fetch_stats("primary")
+    assert stats["rays"] == exact["rays"] == 320 * 180 and stats["hits"] == exact["hits"]
+    assert stats["lookups"] < 0.6 * exact["t_in"]

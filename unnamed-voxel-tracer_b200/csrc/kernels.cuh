@@ -193,7 +193,7 @@ struct WorldArgs<WorldCompact> {
 };
 
 // ---- primary pass ------------------------------------------------------------------------
-template <class World, int COUNT, bool HITBUF>
+template <class World, int COUNT, bool HITBUF, bool BATCH>
 __global__ void __launch_bounds__(kThreads) primary_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0,
                                                            ViewDev v, GBufDev gb, DevCounters *counters) {
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kThreads) primary_kernel(WorldArgs<World> wa, 
     uint32_t x, ly, y;
     tile_pixel(x, ly);
     const bool valid = v.global_row(ly, y) && x < v.W;
-    const CamDev &cam = cams ? cams[blockIdx.z] : cam0;
+    const CamDev &cam = BATCH ? cams[blockIdx.z] : cam0;  // single camera: straight from the parameter bank
 
     TripCounts tc = {0, 0, 0};
     uint32_t is_hit = 0;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) shade_kernel(ViewDev v, GBufDev gb, Frame
 // ---- fused frame: primary + secondary + shade in one launch -------------------------------
 // Results are identical to the three separate passes: the shadow ray starts from the same
 // quantised position/normal the G-buffer would hold.
-template <class World, bool GBUF>
+template <class World, bool GBUF, bool BATCH>
 __global__ void __launch_bounds__(kThreads) frame_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0, ViewDev v,
                                                          uint32_t shadow_steps, GBufDev gb, FrameTarget ft) {
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(kThreads) frame_kernel(WorldArgs<World> wa, co
     uint32_t x, ly, y;
     tile_pixel(x, ly);
     const bool valid = v.global_row(ly, y) && x < v.W;
-    const CamDev &cam = cams ? cams[blockIdx.z] : cam0;
+    const CamDev &cam = BATCH ? cams[blockIdx.z] : cam0;
     float dx = 0.0f, dy = 0.0f, dz = 1.0f, sx = 0.0f, sy = 0.0f, sz = 0.0f;
     if (valid) primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
     Hit h;

@@ -79,6 +79,8 @@ struct WorldCompact {
     uint32_t cd;
     uint32_t cd1;                           // cd + 1: stride of chunks2 (one guard layer on the high side)
     uint32_t n_real_bricks;                 // bricks [0, n_real) mirror reference bricks; the rest only carry clearances
+    int32_t y_clear;                        // every block with y >= y_clear is empty (max occupied block y + 1)
+    int32_t dim;                            // MAP_DIMENSION in blocks
 
     __device__ __forceinline__ uint32_t block_at(uint32_t px, uint32_t py, uint32_t pz, bool &chunk_hit) const {
         const uint32_t bx = px >> 3, by = py >> 3, bz = pz >> 3;
@@ -298,6 +300,13 @@ __device__ __forceinline__ void dda_step_last(int &gx, int &gy, int &gz, float &
 //    divergence-free, branch-free DDA loop with a uniform trip count, then the lanes whose free
 //    trips ran out look up again.  Lanes whose ray has ended keep executing the arithmetic on dead
 //    state (no memory traffic) and are parked with limit = kDead.
+//  * SEALED RAYS.  A ray whose remaining trips are all provably empty AND inside the map ends as the
+//    reference's iteration-cap miss (data 0, trips = maxSteps) whatever its arithmetic would have
+//    been, so it is retired at once: (a) trip + 1 + n_free >= maxSteps, or (b) the ray climbs
+//    (dir.y > 0), its block row is above every occupied block of the world, and no map face in its
+//    direction of travel is within maxSteps + 2 blocks (one block per trip at most).  Sky rays stop
+//    marching as soon as they clear the terrain.  Only a lookup that found an EMPTY block can seal
+//    (the current trip's own block must still be tested).  (COUNT == 1 never seals: exact counters.)
 //  * the guard layer of chunks2 (index cd on any axis) removes the chunk-range test: `pos` can
 //    exceed the map by at most one block on the high side while g is in bounds.
 //  * sub-voxel occupancy is a bit test in shared memory; colour and block word are fetched once,
@@ -349,35 +358,66 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
         if (COUNT) tc.t_in = tc.t_chunk = tc.t_block = 0;
     }
 
+    // no map face in the direction of travel within reach of the remaining trips (one block per trip)
+    const int reach = max_steps + 2;
+    const bool no_exit = (posx ? w.dim - 1 - (gx >> 3) : (gx >> 3)) >= reach && (posy ? w.dim - 1 - (gy >> 3) : (gy >> 3)) >= reach &&
+                         (posz ? w.dim - 1 - (gz >> 3) : (gz >> 3)) >= reach;
+    const bool climbs = COUNT != 1 && posy && no_exit;
+
     const uint32_t cd1 = w.cd1;
     int trip = 0;                     // warp-uniform
     int limit = fast ? 0 : kDead;     // trips in [trip, limit) need no lookup; kDead parks the lane
     bool mx = true, my = false;       // minIdx of the previous trip == 0 / == 1 (starts at 0, map.glsl:98)
 
+    uint32_t cmat = 0;  // material of the block looked up last (0: none) — sub-voxel steps mostly stay inside it
+
     for (;;) {
-        // ---- lookups for the lanes whose free trips ran out (map.glsl:107-144) ------------
-        if (trip >= limit) {
+        // ---- lookups (map.glsl:107-144) --------------------------------------------------
+        // A round is paid for by the whole warp, so EVERY live lane looks up, not only the ones whose
+        // free trips ran out: a lane still inside its free run re-reads an (empty) block and refreshes
+        // its clearance from the new position, which keeps the lanes' lookups aligned (fewer rounds).
+        if (limit < kDead) {
             if ((unsigned)gx >= (unsigned)bound || (unsigned)gy >= (unsigned)bound || (unsigned)gz >= (unsigned)bound) {
                 out.exit_kind = 2;
                 out.trips = (uint32_t)trip;
+                out.px = out.py = out.pz = 0xFFFFFFFFu;
                 limit = kDead;
             } else {
                 if (COUNT == 2) tc.t_in++;  // lookups performed
                 const uint32_t px = (uint32_t)gx + __float2uint_rz(wx);
                 const uint32_t py = (uint32_t)gy + __float2uint_rz(wy);
                 const uint32_t pz = (uint32_t)gz + __float2uint_rz(wz);
-                const uint32_t e = __ldg(&w.chunks2[(px >> 6) + cd1 * ((py >> 6) + (pz >> 6) * cd1)]);
-                int code;  // brick byte semantics: < kMatLimit material, else kMatLimit + n_free
-                if ((int)e < 0) {
-                    code = (int)(e & 0xFFu) + (int)kMatLimit;
+                uint32_t mat;
+                int n_free = 0;
+                // out.p* hold the `pos` of the previous lookup: still inside that (non-empty) block?
+                if (!big && cmat != 0u && (((px ^ out.px) | (py ^ out.py) | (pz ^ out.pz)) < 8u)) {
+                    mat = cmat;
+                    if (COUNT == 1) tc.t_chunk++;
                 } else {
-                    if (COUNT == 1 && e < w.n_real_bricks) tc.t_chunk++;
-                    code = (int)__ldg(&w.bricks8[e * 512u + (((px >> 3) & 7u) | (py & 0x38u) | ((pz & 0x38u) << 3))]);
+                    const uint32_t e = __ldg(&w.chunks2[(px >> 6) + cd1 * ((py >> 6) + (pz >> 6) * cd1)]);
+                    if ((int)e < 0) {
+                        n_free = (int)(e & 0xFFu);
+                        mat = 0u;
+                    } else {
+                        if (COUNT == 1 && e < w.n_real_bricks) tc.t_chunk++;
+                        const uint32_t b8 = __ldg(&w.bricks8[e * 512u + (((px >> 3) & 7u) | (py & 0x38u) | ((pz & 0x38u) << 3))]);
+                        const bool is_mat = b8 < kMatLimit;
+                        n_free = is_mat ? 0 : (int)(b8 - kMatLimit);
+                        mat = is_mat ? b8 : 0u;
+                    }
+                    cmat = mat;
                 }
-                const int n_free = (COUNT == 1) ? 0 : max(code - (int)kMatLimit, 0);  // exact counters need every lookup
-                limit = trip + 1 + n_free;
-                if (code < (int)kMatLimit && code != 0) {  // a block: test the sub-voxel
-                    const uint32_t mat = (uint32_t)code;
+                out.px = px; out.py = py; out.pz = pz;
+                if (COUNT == 1) n_free = 0;  // exact reference counters need every lookup
+                limit = max(limit, trip + 1 + n_free);  // an earlier guarantee stays valid
+                const bool seal = COUNT != 1 && mat == 0u && (limit >= max_steps || (climbs && (gy >> 3) >= w.y_clear));
+                limit = min(limit, max_steps);
+                if (seal) {
+                    // sealed: nothing but empty in-map blocks until the iteration cap (map.glsl:167)
+                    out.trips = (uint32_t)max_steps;
+                    out.px = out.py = out.pz = 0xFFFFFFFFu;
+                    limit = kDead;
+                } else if (mat != 0u) {  // a block: test the sub-voxel
                     if (COUNT == 1) tc.t_block++;
                     const uint32_t bit = (px & 7u) | ((py & 7u) << 3) | ((pz & 7u) << 6);
                     const uint32_t word = w.smem_masks[mat * 16u + (bit >> 5)];
@@ -387,7 +427,6 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
                         out.hx = (float)gx + wx;
                         out.hy = (float)gy + wy;
                         out.hz = (float)gz + wz;
-                        out.px = px; out.py = py; out.pz = pz;
                         out.block = __ldg(&w.mat_word[mat]);
                         out.exit_kind = 0;
                         out.trips = (uint32_t)trip + 1u;
@@ -420,9 +459,9 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
         }
 
         // ---- how many trips can the whole warp run without a lookup? ----------------------
-        int k = __reduce_min_sync(0xFFFFFFFFu, limit - trip);
-        if (k >= kDead / 2) break;             // no live lane left
-        k = min(k, max_steps - trip);          // max_steps > 0 on every live lane
+        // live lanes: 1 <= limit - trip (limit is clamped to max_steps > trip); parked lanes: huge
+        const int k = __reduce_min_sync(0xFFFFFFFFu, limit - trip);
+        if (k >= kDead / 2) break;  // no live lane left
 
         // ---- k DDA steps, branch-free (map.glsl:157-162) -----------------------------------
         for (int j = 1; j < k; ++j) dda_step(gx, gy, gz, wx, wy, wz, isx, isy, isz, tgx, tgy, tgz, invx, invy, invz, dx, dy, dz, rsx, rsy, rsz);
@@ -433,8 +472,11 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
             my = myi != 0;
         }
         trip += k;
-        if (trip >= max_steps) {  // iteration cap: miss (map.glsl:167)
-            if (limit < kDead) out.trips = (uint32_t)trip;
+        if (trip >= max_steps) {  // iteration cap: miss (map.glsl:167); in lockstep it ends every live lane at once
+            if (limit < kDead) {
+                out.trips = (uint32_t)trip;
+                out.px = out.py = out.pz = 0xFFFFFFFFu;
+            }
             break;
         }
     }

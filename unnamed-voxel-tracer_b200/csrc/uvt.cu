@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -48,6 +49,7 @@ struct uvt_ctx {
     size_t d_brick8_capacity = 0;
     uint32_t *d_chunks2 = nullptr;  // fast-path chunk table [(cd+1)^3]
     size_t n_total_bricks = 0;      // real + virtual (clearance-only) bricks in d_bricks8
+    int32_t y_clear = 0;            // max occupied block y + 1 (every block at or above is empty)
     bool world_committed = false;
 
     // ---- atlas: host copy by slot (slot = x/8 + 32*(y/8) + 1024*(z/8)), device [n_slots][512]
@@ -240,6 +242,8 @@ WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     a.w.chunks2 = c->d_chunks2;
     a.w.cd1 = c->cd + 1;
     a.w.n_real_bricks = (uint32_t)c->n_bricks;
+    a.w.y_clear = c->y_clear;
+    a.w.dim = (int32_t)c->dim;
     a.w.bricks8 = c->d_bricks8;
     a.w.mat_word = c->d_mat_word;
     a.w.mat_color = c->d_mat_color;
@@ -309,22 +313,23 @@ int pre_dispatch(uvt_ctx *c) {
     return ensure_ready(c);
 }
 
+template <class World, int COUNT>
+void launch_primary_world(uvt_ctx *c, const WorldArgs<World> &wa, const ViewDev &v, const GBufDev &g, dim3 grid) {
+    const bool hb = c->d_hit != nullptr, batch = c->layers > 1;
+    const CamDev *cams = c->d_cams;
+#define UVT_LAUNCH(HB, BATCH) primary_kernel<World, COUNT, HB, BATCH><<<grid, kThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters)
+    if (hb) { if (batch) UVT_LAUNCH(true, true); else UVT_LAUNCH(true, false); }
+    else { if (batch) UVT_LAUNCH(false, true); else UVT_LAUNCH(false, false); }
+#undef UVT_LAUNCH
+}
+
 template <int COUNT>
 int launch_primary(uvt_ctx *c) {
     const ViewDev v = make_view(c, c->params.primary_max_steps);
     const GBufDev g = make_gbuf(c);
     const dim3 grid = trace_grid(c);
-    const CamDev *cams = c->layers > 1 ? c->d_cams : nullptr;
-    const bool hb = c->d_hit != nullptr;
-    if (use_compact(c)) {
-        auto wa = world_compact(c);
-        if (hb) primary_kernel<WorldCompact, COUNT, true><<<grid, kThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters);
-        else primary_kernel<WorldCompact, COUNT, false><<<grid, kThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters);
-    } else {
-        auto wa = world_ref(c);
-        if (hb) primary_kernel<WorldRef, COUNT, true><<<grid, kThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters);
-        else primary_kernel<WorldRef, COUNT, false><<<grid, kThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters);
-    }
+    if (use_compact(c)) launch_primary_world<WorldCompact, COUNT>(c, world_compact(c), v, g, grid);
+    else launch_primary_world<WorldRef, COUNT>(c, world_ref(c), v, g, grid);
     return check_launch(c, "primary_kernel");
 }
 
@@ -544,7 +549,7 @@ int uvt_pipeline_create(uvt_ctx *c, uvt_pipeline_kind kind, uvt_pipeline **out) 
     cudaFuncAttributes fa;
     const void *fn = nullptr;
     switch (kind) {
-        case UVT_PIPELINE_PRIMARY: fn = (const void *)primary_kernel<WorldCompact, 0, false>; break;
+        case UVT_PIPELINE_PRIMARY: fn = (const void *)primary_kernel<WorldCompact, 0, false, false>; break;
         case UVT_PIPELINE_SECONDARY: fn = (const void *)secondary_kernel<WorldCompact, 0>; break;
         case UVT_PIPELINE_EDIT: fn = (const void *)pick_kernel<WorldCompact>; break;
         case UVT_PIPELINE_BLIT: fn = (const void *)shade_kernel; break;
@@ -657,6 +662,24 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
     }
     c->compact_ok = !overflow;
     if (c->compact_ok) {
+        // highest occupied block row: chunk y of every brick + the highest non-empty local y inside it
+        int32_t top = -1;
+        const size_t cdz = c->cd;
+        for (size_t i = 0; i < n_chunks; ++i) {
+            const uint32_t e = c->h_chunks[i];
+            if (e == 0) continue;
+            const int32_t cy = (int32_t)((i / cdz) % cdz);
+            if (cy * 8 + 7 <= top) continue;
+            const uint32_t *bw = c->h_bricks + (size_t)(e - 1) * 512;
+            for (int ly = 7; ly >= 0 && cy * 8 + ly > top; --ly) {
+                bool any = false;
+                for (int lz = 0; lz < 8 && !any; ++lz)
+                    for (int lx = 0; lx < 8; ++lx)
+                        if (bw[lx + 8 * ly + 64 * lz] != 0) { any = true; break; }
+                if (any) { top = cy * 8 + ly; break; }
+            }
+        }
+        c->y_clear = top + 1;
         int rc = build_compact(c, n_bricks, n_words);
         if (rc != UVT_OK) return rc;
     }
@@ -784,10 +807,16 @@ int uvt_dispatch_frame(uvt_ctx *c) {
     const dim3 grid = trace_grid(c);
     const CamDev *cams = c->layers > 1 ? c->d_cams : nullptr;
     PassTimer t(c, 3);
-    if (use_compact(c))
-        frame_kernel<WorldCompact, true><<<grid, kThreads, 0, c->stream>>>(world_compact(c), cams, c->cam0, v, c->params.shadow_max_steps, g, make_target(c));
-    else
-        frame_kernel<WorldRef, true><<<grid, kThreads, 0, c->stream>>>(world_ref(c), cams, c->cam0, v, c->params.shadow_max_steps, g, make_target(c));
+    const bool batch = c->layers > 1;
+    const uint32_t ss = c->params.shadow_max_steps;
+    const FrameTarget ft = make_target(c);
+    if (use_compact(c)) {
+        if (batch) frame_kernel<WorldCompact, true, true><<<grid, kThreads, 0, c->stream>>>(world_compact(c), cams, c->cam0, v, ss, g, ft);
+        else frame_kernel<WorldCompact, true, false><<<grid, kThreads, 0, c->stream>>>(world_compact(c), cams, c->cam0, v, ss, g, ft);
+    } else {
+        if (batch) frame_kernel<WorldRef, true, true><<<grid, kThreads, 0, c->stream>>>(world_ref(c), cams, c->cam0, v, ss, g, ft);
+        else frame_kernel<WorldRef, true, false><<<grid, kThreads, 0, c->stream>>>(world_ref(c), cams, c->cam0, v, ss, g, ft);
+    }
     return check_launch(c, "frame_kernel");
 }
 
