@@ -148,8 +148,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path) or (_build.is_stale() and os.environ.get("UVT_NO_REBUILD") != "1"):
+    path = os.environ.get("UVT_LIB_PATH") or _build.LIB  # UVT_LIB_PATH: an experimental variant built by build.build(out=...)
+    if path == _build.LIB and (not os.path.exists(path) or (_build.is_stale() and os.environ.get("UVT_NO_REBUILD") != "1")):
         _build.build()
     L = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():

@@ -52,17 +52,19 @@ def is_stale():
     return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS + [os.path.abspath(__file__)])
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out/defines: build an experimental variant (e.g. -DUVT_WARP_W=4) next to the product library."""
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    out = out or LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("nvcc failed building libuvt.so")
     if verbose:
         print(r.stdout)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

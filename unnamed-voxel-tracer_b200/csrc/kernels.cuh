@@ -161,13 +161,25 @@ __device__ __forceinline__ void warp_add(unsigned long long *dst, uint32_t v) {
     if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, (unsigned long long)v);
 }
 
-// CTA tile: 128 threads = 4 warps; a warp covers 8x4 pixels, the CTA 16x8.
-constexpr int kTileW = 16, kTileH = 8, kThreads = 128;
+// CTA tile: 128 threads = 4 warps in a 2x2 arrangement; a warp covers kWarpW x kWarpH pixels (8x4 by default:
+// the most coherent footprint, SIMT efficiency 97.8 % at trip granularity), the CTA 2*kWarpW x 2*kWarpH.
+#ifndef UVT_WARP_W
+#define UVT_WARP_W 8
+#endif
+#ifndef UVT_MIN_BLOCKS
+#define UVT_MIN_BLOCKS 10  // <= 51 registers: 40 warps/SM; measured best of {1, 6, 10, 12} on the 1080p primary pass
+#endif
+#ifndef UVT_MIN_BLOCKS_FRAME
+#define UVT_MIN_BLOCKS_FRAME 7  // the fused frame kernel keeps two rays' worth of state: <= 73 registers measured faster than <= 51
+#endif
+constexpr int kWarpW = UVT_WARP_W, kWarpH = 32 / UVT_WARP_W;
+constexpr int kTileW = 2 * kWarpW, kTileH = 2 * kWarpH, kThreads = 128;
+static_assert(kWarpW * kWarpH == 32, "a warp covers 32 pixels");
 
 __device__ __forceinline__ void tile_pixel(uint32_t &x, uint32_t &ly) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    x = blockIdx.x * kTileW + (warp & 1u) * 8u + (lane & 7u);
-    ly = blockIdx.y * kTileH + (warp >> 1) * 4u + (lane >> 3);
+    x = blockIdx.x * kTileW + (warp & 1u) * kWarpW + (lane % kWarpW);
+    ly = blockIdx.y * kTileH + (warp >> 1) * kWarpH + (lane / kWarpW);
 }
 
 __device__ __forceinline__ void stage_masks(uint32_t *smem, const uint32_t *__restrict__ gmasks, uint32_t n_mats) {
@@ -194,7 +206,7 @@ struct WorldArgs<WorldCompact> {
 
 // ---- primary pass ------------------------------------------------------------------------
 template <class World, int COUNT, bool HITBUF, bool BATCH>
-__global__ void __launch_bounds__(kThreads) primary_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0,
+__global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) primary_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0,
                                                            ViewDev v, GBufDev gb, DevCounters *counters) {
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
     World w = wa.w;
@@ -265,7 +277,7 @@ __device__ __forceinline__ uint32_t shadow_pixel(const World &w, bool active, co
 
 // ---- secondary pass ------------------------------------------------------------------------
 template <class World, int COUNT>
-__global__ void __launch_bounds__(kThreads) secondary_kernel(WorldArgs<World> wa, ViewDev v, GBufDev gb, DevCounters *counters) {
+__global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) secondary_kernel(WorldArgs<World> wa, ViewDev v, GBufDev gb, DevCounters *counters) {
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
     World w = wa.w;
     if constexpr (std::is_same<World, WorldCompact>::value) {
@@ -346,7 +358,7 @@ __global__ void __launch_bounds__(256) shade_kernel(ViewDev v, GBufDev gb, Frame
 // Results are identical to the three separate passes: the shadow ray starts from the same
 // quantised position/normal the G-buffer would hold.
 template <class World, bool GBUF, bool BATCH>
-__global__ void __launch_bounds__(kThreads) frame_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0, ViewDev v,
+__global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS_FRAME) frame_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0, ViewDev v,
                                                          uint32_t shadow_steps, GBufDev gb, FrameTarget ft) {
     __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
     World w = wa.w;

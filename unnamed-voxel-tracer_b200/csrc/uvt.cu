@@ -756,7 +756,7 @@ int uvt_resize(uvt_ctx *c, uint32_t width, uint32_t height) {
 int uvt_set_partition(uvt_ctx *c, uint32_t band_rows, uint32_t n_parts, uint32_t part) {
     if (!c) return UVT_ERR_INVALID;
     UVT_REQUIRE(c, n_parts >= 1 && part < n_parts, "part must be < n_parts");
-    UVT_REQUIRE(c, band_rows >= kTileH && band_rows % kTileH == 0, "band_rows must be a positive multiple of 8");
+    UVT_REQUIRE(c, band_rows >= 8 && band_rows % 8 == 0 && band_rows % kTileH == 0, "band_rows must be a positive multiple of 8 (and of the CTA tile height)");
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->band_rows = band_rows;
     c->n_parts = n_parts;
