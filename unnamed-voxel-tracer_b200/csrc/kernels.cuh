@@ -559,6 +559,36 @@ __global__ void brick_rowmask_kernel(const uint8_t *__restrict__ bricks8, size_t
     rowmask[i] = (uint8_t)m;
 }
 
+// Column tops for sky_sealed(): tops32[x + dim*z] = highest occupied block y + 1 of the column (0: empty column).
+// One CTA per real brick, one thread per (x, z) column of the brick; run on material bytes (before the clearances are written).
+__global__ void __launch_bounds__(64) column_tops_kernel(const uint8_t *__restrict__ bricks8, const uint32_t *__restrict__ brick_chunk, int cd,
+                                                         unsigned int *__restrict__ tops32) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t cj = brick_chunk[b];
+    const int cx = (int)(cj % cd), cy = (int)((cj / cd) % cd), cz = (int)(cj / ((uint32_t)cd * cd));
+    const int lx = threadIdx.x & 7, lz = threadIdx.x >> 3;
+    const int dim = cd * 8;
+    for (int ly = 7; ly >= 0; --ly) {
+        const uint8_t v = bricks8[(size_t)b * 512u + lx + 8 * ly + 64 * lz];
+        if (v != 0 && v < kMatLimit) {
+            atomicMax(&tops32[(size_t)(cx * 8 + lx) + (size_t)dim * (cz * 8 + lz)], (unsigned int)(cy * 8 + ly + 1));
+            break;
+        }
+    }
+}
+
+// clear4[qx + (dim/4)*qz] = max of tops32 over the 4x4-block group grown by one block on every side
+__global__ void quad_clear_kernel(const unsigned int *__restrict__ tops32, uint16_t *__restrict__ clear4, int dim) {
+    const int qdim = dim >> 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= qdim * qdim) return;
+    const int qx = i % qdim, qz = i / qdim;
+    unsigned int m = 0;
+    for (int z = max(4 * qz - 1, 0); z <= min(4 * qz + 4, dim - 1); ++z)
+        for (int x = max(4 * qx - 1, 0); x <= min(4 * qx + 4, dim - 1); ++x) m = max(m, tops32[(size_t)x + (size_t)dim * z]);
+    clear4[i] = (uint16_t)m;
+}
+
 // Block-level clearance.  One CTA per brick, one thread per block.  The occupancy of the 5x5x5 chunk
 // neighbourhood is staged in shared memory as 40x40 rows of 40 x-bits (out-of-map = occupied); each
 // empty block searches growing Chebyshev shells for the nearest occupied block, D capped at 16, and

@@ -81,6 +81,8 @@ struct WorldCompact {
     uint32_t n_real_bricks;                 // bricks [0, n_real) mirror reference bricks; the rest only carry clearances
     int32_t y_clear;                        // every block with y >= y_clear is empty (max occupied block y + 1)
     int32_t dim;                            // MAP_DIMENSION in blocks
+    const uint16_t *__restrict__ clear4;    // [(dim/4)^2] per 4x4-block column group, grown by one block on every side:
+                                            // every block with y >= clear4 there is empty (sky_sealed)
 
     __device__ __forceinline__ uint32_t block_at(uint32_t px, uint32_t py, uint32_t pz, bool &chunk_hit) const {
         const uint32_t bx = px >> 3, by = py >> 3, bz = pz >> 3;
@@ -198,6 +200,39 @@ __device__ __forceinline__ void trace_map(const World &w, float ox, float oy, fl
     out.trips = (uint32_t)trip;
 }
 
+// ---- conservative "nothing ahead" test for climbing rays -------------------------------------
+// A ray with dir.y > 0 whose straight line stays at least two blocks above every occupied block of the
+// 4x4-block column groups it passes over (each grown by one block sideways, clear4) cannot meet a
+// non-empty block: the reference DDA follows that line to within a fraction of a block (0.999 resets,
+// fp32 rounding) and looks up `pos` at most one block beside it.  The test walks the column groups with
+// a 2-D DDA until the line has covered more blocks (L1) than the remaining trips can cross, or has risen
+// above the whole world.  It decides only WHETHER lookups can be skipped, never a hit, so it needs no
+// bit-exact arithmetic.  (px, py, pz) in blocks, d = the ray direction with zero components patched.
+__device__ __noinline__ bool sky_sealed(const uint16_t *__restrict__ clear4, int dim, int y_clear, float px, float py, float pz,
+                                        float dx, float dy, float dz, int trips_left) {
+    const float inv_dx = 1.0f / dx, inv_dz = 1.0f / dz;
+    int qx = (int)(px * 0.25f), qz = (int)(pz * 0.25f);
+    const int qdim = dim >> 2;
+    const int sx = dx > 0.0f ? 1 : -1, sz = dz > 0.0f ? 1 : -1;
+    float tmx = ((float)((qx + (dx > 0.0f ? 1 : 0)) * 4) - px) * inv_dx;  // line parameter at the next x / z group boundary
+    float tmz = ((float)((qz + (dz > 0.0f ? 1 : 0)) * 4) - pz) * inv_dz;
+    const float tdx = 4.0f * fabsf(inv_dx), tdz = 4.0f * fabsf(inv_dz);
+    // each trip crosses one block boundary, so after n trips the line has covered about n blocks in L1
+    const float t_stop = (float)(trips_left + 4) / (fabsf(dx) + fabsf(dy) + fabsf(dz));
+    const float y_all = (float)y_clear + 2.0f;
+    float t = 0.0f;
+    for (int it = 0; it < 96; ++it) {
+        if ((unsigned)qx >= (unsigned)qdim || (unsigned)qz >= (unsigned)qdim) return false;
+        const float y_in = py + dy * t;  // lowest height of the line inside this group (it climbs)
+        if (y_in - 2.0f < (float)__ldg(&clear4[qx + qdim * qz])) return false;
+        if (y_in >= y_all) return true;  // above every occupied block of the world
+        if (tmx < tmz) { t = tmx; tmx += tdx; qx += sx; }
+        else { t = tmz; tmz += tdz; qz += sz; }
+        if (t > t_stop) return true;
+    }
+    return false;
+}
+
 // One DDA step (map.glsl:157-162), hand-scheduled and branch-free: 6 ops for t, 3 compares, min3,
 // 6 ops for within += dir * t[minIdx], then the stepped axis is reset / advanced under its predicate.
 // .rn ops are never contracted.  t[minIdx] is the minimum of the three (ties carry equal values;
@@ -304,8 +339,10 @@ __device__ __forceinline__ void dda_step_last(int &gx, int &gy, int &gz, float &
 //    reference's iteration-cap miss (data 0, trips = maxSteps) whatever its arithmetic would have
 //    been, so it is retired at once: (a) trip + 1 + n_free >= maxSteps, or (b) the ray climbs
 //    (dir.y > 0), its block row is above every occupied block of the world, and no map face in its
-//    direction of travel is within maxSteps + 2 blocks (one block per trip at most).  Sky rays stop
-//    marching as soon as they clear the terrain.  Only a lookup that found an EMPTY block can seal
+//    direction of travel is within maxSteps + 2 blocks (one block per trip at most), or (c) the ray
+//    climbs and sky_sealed() proves its line stays two blocks above the terrain it passes over.
+//    (c) is tried by the whole warp together at trips 0, 4, 8, 16, ... (a failed test is cheap).  Sky
+//    and sun-shadow rays stop marching as soon as they clear the terrain.  Only a lookup that found an EMPTY block can seal
 //    (the current trip's own block must still be tested).  (COUNT == 1 never seals: exact counters.)
 //  * the guard layer of chunks2 (index cd on any axis) removes the chunk-range test: `pos` can
 //    exceed the map by at most one block on the high side while g is in bounds.
@@ -368,10 +405,22 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
     int trip = 0;                     // warp-uniform
     int limit = fast ? 0 : kDead;     // trips in [trip, limit) need no lookup; kDead parks the lane
     bool mx = true, my = false;       // minIdx of the previous trip == 0 / == 1 (starts at 0, map.glsl:98)
+    int next_try = 0;                 // warp-uniform: next trip at which climbing lanes try sky_sealed()
 
     uint32_t cmat = 0;  // material of the block looked up last (0: none) — sub-voxel steps mostly stay inside it
 
     for (;;) {
+        // ---- sealed-ray test (c), all candidate lanes of the warp at once ------------------
+        if (trip >= next_try) {
+            next_try = next_try ? 2 * next_try : 4;
+            if (climbs && limit < kDead && (big || trip == 0) &&
+                sky_sealed(w.clear4, w.dim, w.y_clear, ((float)gx + wx) * 0.125f, ((float)gy + wy) * 0.125f, ((float)gz + wz) * 0.125f, dx, dy, dz, max_steps - trip)) {
+                out.trips = (uint32_t)max_steps;  // iteration-cap miss (map.glsl:167)
+                out.px = out.py = out.pz = 0xFFFFFFFFu;
+                limit = kDead;
+            }
+        }
+
         // ---- lookups (map.glsl:107-144) --------------------------------------------------
         // A round is paid for by the whole warp, so EVERY live lane looks up, not only the ones whose
         // free trips ran out: a lane still inside its free run re-reads an (empty) block and refreshes

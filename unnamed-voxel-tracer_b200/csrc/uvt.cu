@@ -50,6 +50,7 @@ struct uvt_ctx {
     uint32_t *d_chunks2 = nullptr;  // fast-path chunk table [(cd+1)^3]
     size_t n_total_bricks = 0;      // real + virtual (clearance-only) bricks in d_bricks8
     int32_t y_clear = 0;            // max occupied block y + 1 (every block at or above is empty)
+    uint16_t *d_clear4 = nullptr;   // [(dim/4)^2] dilated column-group tops for sky_sealed()
     bool world_committed = false;
 
     // ---- atlas: host copy by slot (slot = x/8 + 32*(y/8) + 1024*(z/8)), device [n_slots][512]
@@ -244,6 +245,7 @@ WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     a.w.n_real_bricks = (uint32_t)c->n_bricks;
     a.w.y_clear = c->y_clear;
     a.w.dim = (int32_t)c->dim;
+    a.w.clear4 = c->d_clear4;
     a.w.bricks8 = c->d_bricks8;
     a.w.mat_word = c->d_mat_word;
     a.w.mat_color = c->d_mat_color;
@@ -351,9 +353,9 @@ int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
     const size_t n2 = (size_t)(cd + 1) * (cd + 1) * (cd + 1);
     uint8_t *f0 = nullptr, *f1 = nullptr, *rowmask = nullptr, *d_vals = nullptr;
     uint32_t *d_keys = nullptr, *brick_chunk = nullptr;
-    unsigned int *d_counter = nullptr;
+    unsigned int *d_counter = nullptr, *tops32 = nullptr;
     auto cleanup = [&]() {
-        cudaFree(f0); cudaFree(f1); cudaFree(rowmask); cudaFree(d_vals); cudaFree(d_keys); cudaFree(brick_chunk); cudaFree(d_counter);
+        cudaFree(f0); cudaFree(f1); cudaFree(rowmask); cudaFree(d_vals); cudaFree(d_keys); cudaFree(brick_chunk); cudaFree(d_counter); cudaFree(tops32);
     };
 #define UVT_CUDA_C(expr)                                                                                      \
     do {                                                                                                      \
@@ -394,6 +396,7 @@ int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
     UVT_CUDA_C(cudaMemsetAsync(d_counter, 0, 4, c->stream));
     build_chunks2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(c->d_chunks, f0, c->d_chunks2, brick_chunk, cd, (uint32_t)n_bricks, d_counter);
     c->launches++;
+    UVT_CUDA_C(cudaMemsetAsync(c->d_clear4, 0, (size_t)(c->dim / 4) * (c->dim / 4) * 2, c->stream));  // empty world: nothing above y = 0
     if (n_total) {
         UVT_CUDA_C(cudaMemsetAsync(c->d_bricks8, 0, n_total * 512, c->stream));
         if (n_bricks) {
@@ -414,6 +417,15 @@ int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
             repack_bricks_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_bricks, c->d_bricks8, n_words, d_keys, d_vals, lut_mask);
             c->launches++;
             UVT_CUDA_C(cudaStreamSynchronize(c->stream));  // keys/vals staging dies at scope exit
+        }
+        {   // column tops -> dilated 4x4 column-group tops (sky_sealed)
+            const size_t ncol = (size_t)c->dim * c->dim;
+            UVT_CUDA_C(cudaMalloc(&tops32, ncol * 4));
+            UVT_CUDA_C(cudaMemsetAsync(tops32, 0, ncol * 4, c->stream));
+            if (n_bricks) column_tops_kernel<<<(unsigned)n_bricks, 64, 0, c->stream>>>(c->d_bricks8, brick_chunk, cd, tops32);
+            const int nq = (int)((c->dim / 4) * (c->dim / 4));
+            quad_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(tops32, c->d_clear4, (int)c->dim);
+            c->launches += 2;
         }
         UVT_CUDA_C(cudaMalloc(&rowmask, n_total * 64));
         const size_t n_rows = n_total * 64;
@@ -496,7 +508,7 @@ void uvt_destroy(uvt_ctx *c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     free_gbuffer(c);
     cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
-    cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2);
+    cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
     cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame);
     for (int i = 0; i < 4; ++i)
@@ -584,10 +596,11 @@ int uvt_world_alloc(uvt_ctx *c, uint32_t dim, uint32_t **chunks_host, uint32_t *
     UVT_REQUIRE(c, brick_capacity > 0, "brick_capacity must be > 0");
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
-    cudaFree(c->d_chunks); cudaFree(c->d_chunks2);
+    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4);
     c->h_chunks = c->h_bricks = nullptr;
     c->d_chunks = nullptr;
     c->d_chunks2 = nullptr;
+    c->d_clear4 = nullptr;
     c->dim = dim;
     c->cd = dim / 8;
     c->params.map_dim = dim;
@@ -598,6 +611,7 @@ int uvt_world_alloc(uvt_ctx *c, uint32_t dim, uint32_t **chunks_host, uint32_t *
     std::memset(c->h_bricks, 0, brick_capacity * 2048);     // GL zero-initialised storage
     UVT_CUDA(c, cudaMalloc(&c->d_chunks, n_chunks * 4));
     UVT_CUDA(c, cudaMalloc(&c->d_chunks2, (size_t)(c->cd + 1) * (c->cd + 1) * (c->cd + 1) * 4));
+    UVT_CUDA(c, cudaMalloc(&c->d_clear4, (size_t)(dim / 4) * (dim / 4) * 2));
     c->h_capacity = brick_capacity;
     c->n_bricks = 0;
     c->world_committed = false;
