@@ -46,7 +46,8 @@ typedef struct uvt_params {
     float    epsilon;            /* EPSILON 0.001 (assets/shaders/map.glsl:7)    */
     uint32_t flags;              /* UVT_FLAG_*                                    */
     uint32_t layout;             /* uvt_layout: which device world layout the traversal kernels read */
-    uint32_t reserved[9];
+    uint32_t scheduler;          /* uvt_scheduler: how rays are assigned to lanes (B200 layout only) */
+    uint32_t reserved[8];
 } uvt_params;
 
 enum {
@@ -58,6 +59,11 @@ typedef enum uvt_layout {
     UVT_LAYOUT_COMPACT   = 0, /* B200 layout: chunk-occupancy window + 8-bit material bricks + model bitmasks */
     UVT_LAYOUT_REFERENCE = 1  /* the reference SSBO layout read verbatim (u32 chunk table + u32[512] bricks + RGBA8 atlas) */
 } uvt_layout;
+
+typedef enum uvt_scheduler {
+    UVT_SCHED_POOL = 0, /* per-CTA ray pool, compacted between trip phases (default) */
+    UVT_SCHED_TILE = 1  /* one pixel per thread for the whole traversal */
+} uvt_scheduler;
 
 void uvt_default_params(uvt_params *p);
 
@@ -105,6 +111,7 @@ int  uvt_set_stream(uvt_ctx *ctx, void *cuda_stream);
 int  uvt_get_params(uvt_ctx *ctx, uvt_params *out);
 /* Switch the device world layout the traversal kernels read (both stay resident after a commit). */
 int  uvt_set_layout(uvt_ctx *ctx, uint32_t layout);
+int  uvt_set_scheduler(uvt_ctx *ctx, uint32_t scheduler);
 /* The layout actually in use: COMPACT needs <= 255 distinct block words, else REFERENCE is used. */
 int  uvt_effective_layout(uvt_ctx *ctx);
 /* Step caps (reference constants 192 / 48: primary.comp.glsl:43, secondary.comp.glsl:41). */

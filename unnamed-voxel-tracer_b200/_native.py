@@ -21,13 +21,14 @@ UVT_OK = 0
 UVT_ERR_INVALID, UVT_ERR_CUDA, UVT_ERR_NO_DEVICE, UVT_ERR_OOM, UVT_ERR_FORMAT, UVT_ERR_IO = -1, -2, -3, -4, -5, -6
 UVT_FLAG_HIT_BUFFER, UVT_FLAG_ENTITIES = 1, 2
 UVT_LAYOUT_COMPACT, UVT_LAYOUT_REFERENCE = 0, 1
+UVT_SCHED_POOL, UVT_SCHED_TILE = 0, 1
 UVT_PIPELINE_PRIMARY, UVT_PIPELINE_SECONDARY, UVT_PIPELINE_EDIT, UVT_PIPELINE_BLIT = 0, 1, 2, 3
 UVT_BUF_ALBEDO, UVT_BUF_NORMAL, UVT_BUF_POSITION, UVT_BUF_ILLUMINATION, UVT_BUF_FRAME, UVT_BUF_HIT = range(6)
 
 
 class Params(ctypes.Structure):
     _fields_ = [("map_dim", c_u32), ("primary_max_steps", c_u32), ("shadow_max_steps", c_u32), ("edit_max_steps", c_u32),
-                ("epsilon", c_f), ("flags", c_u32), ("layout", c_u32), ("reserved", c_u32 * 9)]
+                ("epsilon", c_f), ("flags", c_u32), ("layout", c_u32), ("scheduler", c_u32), ("reserved", c_u32 * 8)]
 
 
 class Counters(ctypes.Structure):
@@ -57,6 +58,7 @@ SIGNATURES = {
     "uvt_set_stream": (c_int, [c_p, c_p]),
     "uvt_get_params": (c_int, [c_p, P(Params)]),
     "uvt_set_layout": (c_int, [c_p, c_u32]),
+    "uvt_set_scheduler": (c_int, [c_p, c_u32]),
     "uvt_effective_layout": (c_int, [c_p]),
     "uvt_set_max_steps": (c_int, [c_p, c_u32, c_u32]),
     "uvt_pipeline_create": (c_int, [c_p, c_int, P(c_p)]),

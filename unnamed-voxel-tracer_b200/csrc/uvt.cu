@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "pool.cuh"
 
 using namespace uvt;
 
@@ -325,12 +326,31 @@ void launch_primary_world(uvt_ctx *c, const WorldArgs<World> &wa, const ViewDev 
 #undef UVT_LAUNCH
 }
 
+bool use_pool(const uvt_ctx *c) { return use_compact(c) && c->params.scheduler == UVT_SCHED_POOL; }
+
+dim3 pool_grid(const uvt_ctx *c) {
+    const uint32_t rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
+    return dim3((c->W + kPoolTile - 1) / kPoolTile, (rows + kPoolTile - 1) / kPoolTile, c->layers);
+}
+
+template <int COUNT>
+void launch_primary_pool(uvt_ctx *c, const ViewDev &v, const GBufDev &g) {
+    const bool hb = c->d_hit != nullptr, batch = c->layers > 1;
+    const dim3 grid = pool_grid(c);
+    const auto wa = world_compact(c);
+#define UVT_LAUNCH(HB, BATCH) primary_pool_kernel<COUNT, HB, BATCH><<<grid, kThreads, 0, c->stream>>>(wa, c->d_cams, c->cam0, v, g, c->d_counters)
+    if (hb) { if (batch) UVT_LAUNCH(true, true); else UVT_LAUNCH(true, false); }
+    else { if (batch) UVT_LAUNCH(false, true); else UVT_LAUNCH(false, false); }
+#undef UVT_LAUNCH
+}
+
 template <int COUNT>
 int launch_primary(uvt_ctx *c) {
     const ViewDev v = make_view(c, c->params.primary_max_steps);
     const GBufDev g = make_gbuf(c);
     const dim3 grid = trace_grid(c);
-    if (use_compact(c)) launch_primary_world<WorldCompact, COUNT>(c, world_compact(c), v, g, grid);
+    if (use_pool(c)) launch_primary_pool<COUNT>(c, v, g);
+    else if (use_compact(c)) launch_primary_world<WorldCompact, COUNT>(c, world_compact(c), v, g, grid);
     else launch_primary_world<WorldRef, COUNT>(c, world_ref(c), v, g, grid);
     return check_launch(c, "primary_kernel");
 }
@@ -340,7 +360,8 @@ int launch_secondary(uvt_ctx *c) {
     const ViewDev v = make_view(c, c->params.shadow_max_steps);
     const GBufDev g = make_gbuf(c);
     const dim3 grid = trace_grid(c);
-    if (use_compact(c)) secondary_kernel<WorldCompact, COUNT><<<grid, kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
+    if (use_pool(c)) secondary_pool_kernel<COUNT><<<pool_grid(c), kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
+    else if (use_compact(c)) secondary_kernel<WorldCompact, COUNT><<<grid, kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
     else secondary_kernel<WorldRef, COUNT><<<grid, kThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
     return check_launch(c, "secondary_kernel");
 }
@@ -455,6 +476,7 @@ void uvt_default_params(uvt_params *p) {
     p->epsilon = 0.001f;
     p->flags = UVT_FLAG_ENTITIES;
     p->layout = UVT_LAYOUT_COMPACT;
+    p->scheduler = UVT_SCHED_POOL;
 }
 
 int uvt_abi_version(void) { return UVT_ABI_VERSION; }
@@ -537,6 +559,13 @@ int uvt_set_layout(uvt_ctx *c, uint32_t layout) {
     if (!c) return UVT_ERR_INVALID;
     UVT_REQUIRE(c, layout == UVT_LAYOUT_COMPACT || layout == UVT_LAYOUT_REFERENCE, "unknown layout");
     c->params.layout = layout;
+    return UVT_OK;
+}
+
+int uvt_set_scheduler(uvt_ctx *c, uint32_t scheduler) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, scheduler == UVT_SCHED_POOL || scheduler == UVT_SCHED_TILE, "unknown scheduler");
+    c->params.scheduler = scheduler;
     return UVT_OK;
 }
 
@@ -771,6 +800,7 @@ int uvt_set_partition(uvt_ctx *c, uint32_t band_rows, uint32_t n_parts, uint32_t
     if (!c) return UVT_ERR_INVALID;
     UVT_REQUIRE(c, n_parts >= 1 && part < n_parts, "part must be < n_parts");
     UVT_REQUIRE(c, band_rows >= 8 && band_rows % 8 == 0 && band_rows % kTileH == 0, "band_rows must be a positive multiple of 8 (and of the CTA tile height)");
+    UVT_REQUIRE(c, n_parts == 1 || band_rows % kPoolTile == 0, "with more than one part band_rows must be a multiple of 16 (the pooled CTA tile)");
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->band_rows = band_rows;
     c->n_parts = n_parts;
@@ -821,6 +851,16 @@ int uvt_dispatch_frame(uvt_ctx *c) {
     const dim3 grid = trace_grid(c);
     const CamDev *cams = c->layers > 1 ? c->d_cams : nullptr;
     PassTimer t(c, 3);
+    if (use_pool(c)) {
+        // pooled scheduler: the three passes of game.zig:244-255 as three launches (the G-buffer round trip through
+        // L2 costs far less than the lanes a fused pixel-per-thread kernel leaves idle)
+        rc = launch_primary<0>(c);
+        if (rc == UVT_OK) rc = launch_secondary<0>(c);
+        if (rc != UVT_OK) return rc;
+        const uint32_t rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
+        shade_kernel<<<dim3((c->W + 63) / 64, (rows + 3) / 4, c->layers), 256, 0, c->stream>>>(make_view(c, 0), g, make_target(c));
+        return check_launch(c, "shade_kernel");
+    }
     const bool batch = c->layers > 1;
     const uint32_t ss = c->params.shadow_max_steps;
     const FrameTarget ft = make_target(c);

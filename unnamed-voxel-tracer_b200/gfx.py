@@ -88,6 +88,10 @@ class Context:
     def set_layout(self, layout):
         self.check(self.L.uvt_set_layout(self.handle, N.UVT_LAYOUT_COMPACT if layout == "compact" else N.UVT_LAYOUT_REFERENCE))
 
+    def set_scheduler(self, scheduler):
+        """'pool' (per-CTA ray pool with phase-wise compaction, default) or 'tile' (one pixel per thread)."""
+        self.check(self.L.uvt_set_scheduler(self.handle, N.UVT_SCHED_POOL if scheduler == "pool" else N.UVT_SCHED_TILE))
+
     def effective_layout(self):
         return "compact" if self.L.uvt_effective_layout(self.handle) == N.UVT_LAYOUT_COMPACT else "reference"
 
