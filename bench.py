@@ -53,8 +53,10 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--layout", default="compact", choices=["compact", "reference"])
-    ap.add_argument("--scheduler", default="pool", choices=["pool", "tile"],
-                    help="pool = per-CTA ray pool compacted between trip phases (default); tile = one pixel per thread")
+    ap.add_argument("--scheduler", default="tile", choices=["pool", "tile"],
+                    help="tile = one pixel per thread (default); pool = per-CTA ray pool compacted between trip phases")
+    ap.add_argument("--no-dense", action="store_true", help="traverse through chunk table + bricks instead of the dense block grid")
+    ap.add_argument("--split-frame", action="store_true", help="frame = primary + secondary + shade launches instead of the fused kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed steps (reported in config)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
@@ -204,7 +206,7 @@ def run_ours(args):
     dim, W, H, shadows, desc = WORKLOADS[args.workload]
     models = load_models()
 
-    ctx = uvt.Context(local_rank, map_dim=dim, layout=args.layout)
+    ctx = uvt.Context(local_rank, map_dim=dim, layout=args.layout, dense=not args.no_dense, split_frame=args.split_frame)
     ctx.set_scheduler(args.scheduler)
     stream = torch.cuda.Stream(device=local_rank)
     ctx.set_stream(stream.cuda_stream)  # launch on a torch stream so torch.cuda events / NCCL ordering see the work
@@ -392,7 +394,7 @@ def run_ours(args):
             "metric": "rays_per_second", "value": value, "unit": "Grays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if tiled else "weak", "vs_baseline": None,
             "dtype": "f32+i32", "data": "synthetic (procgen world, reference seeds; 29 block models from the reference .vox set)",
-            "config": {"workload": desc, "rays_per_step_all_ranks": rays_all, "layout": ctx.effective_layout(), "scheduler": args.scheduler,
+            "config": {"workload": desc, "rays_per_step_all_ranks": rays_all, "layout": ctx.effective_layout(), "scheduler": args.scheduler, "dense_grid": not args.no_dense,
                        "parallelism": ("interleaved %d-row bands over %d ranks + NCCL gather" % (band, world)) if tiled else
                                       ("poses sharded over %d ranks" % world if sweep else "one independent frame per rank per step, world replicated, no collective"),
                        "l2": "not flushed" if args.no_flush else "flushed between timed steps by a 256 MiB fill (untimed)",

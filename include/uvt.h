@@ -52,7 +52,9 @@ typedef struct uvt_params {
 
 enum {
     UVT_FLAG_HIT_BUFFER = 1u << 0, /* also write the explicit hit buffer (uvt_hit) in the primary pass */
-    UVT_FLAG_ENTITIES   = 1u << 1  /* shadow pass runs traceEntities (map.glsl:172-201); on by default */
+    UVT_FLAG_ENTITIES   = 1u << 1, /* shadow pass runs traceEntities (map.glsl:172-201); on by default */
+    UVT_FLAG_NO_DENSE   = 1u << 2, /* do not use the dense block grid (dim^3 bytes); traverse through chunk table + bricks */
+    UVT_FLAG_SPLIT_FRAME = 1u << 3 /* uvt_dispatch_frame issues the three passes as three launches instead of the fused kernel */
 };
 
 typedef enum uvt_layout {
@@ -61,8 +63,8 @@ typedef enum uvt_layout {
 } uvt_layout;
 
 typedef enum uvt_scheduler {
-    UVT_SCHED_POOL = 0, /* per-CTA ray pool, compacted between trip phases (default) */
-    UVT_SCHED_TILE = 1  /* one pixel per thread for the whole traversal */
+    UVT_SCHED_POOL = 0, /* per-CTA ray pool, compacted between trip phases */
+    UVT_SCHED_TILE = 1  /* one pixel per thread for the whole traversal (default: measured faster) */
 } uvt_scheduler;
 
 void uvt_default_params(uvt_params *p);

@@ -167,7 +167,7 @@ __device__ __forceinline__ void warp_add(unsigned long long *dst, uint32_t v) {
 #define UVT_WARP_W 8
 #endif
 #ifndef UVT_MIN_BLOCKS
-#define UVT_MIN_BLOCKS 10  // <= 51 registers: 40 warps/SM; measured best of {1, 6, 10, 12} on the 1080p primary pass
+#define UVT_MIN_BLOCKS 9  // <= 56 registers, 36 warps/SM: measured best of {7, 8, 9, 10} on the 1080p primary pass (0.353 ms vs 0.374-0.390)
 #endif
 #ifndef UVT_MIN_BLOCKS_FRAME
 #define UVT_MIN_BLOCKS_FRAME 7  // the fused frame kernel keeps two rays' worth of state: <= 73 registers measured faster than <= 51
@@ -183,8 +183,9 @@ __device__ __forceinline__ void tile_pixel(uint32_t &x, uint32_t &ly) {
 }
 
 __device__ __forceinline__ void stage_masks(uint32_t *smem, const uint32_t *__restrict__ gmasks, uint32_t n_mats) {
-    // only the materials in use: (n_mats + 1) x 16 words (id 0 is the empty block)
-    for (uint32_t i = threadIdx.x; i < (n_mats + 1u) * 16u; i += blockDim.x) smem[i] = __ldg(&gmasks[i]);
+    // only the materials in use, at most kSmemMaskMats: (n_mats + 1) x 16 words (id 0 is the empty block)
+    const uint32_t n = min(n_mats + 1u, (uint32_t)kSmemMaskMats) * 16u;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) smem[i] = __ldg(&gmasks[i]);
     __syncthreads();
 }
 
@@ -203,14 +204,20 @@ struct WorldArgs<WorldCompact> {
     const uint32_t *masks;  // global [256][16]
     uint32_t n_mats;        // material ids in use: 1..n_mats
 };
+template <>
+struct WorldArgs<WorldDense> {
+    WorldDense w;
+    const uint32_t *masks;
+    uint32_t n_mats;
+};
 
 // ---- primary pass ------------------------------------------------------------------------
 template <class World, int COUNT, bool HITBUF, bool BATCH>
 __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) primary_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0,
                                                            ViewDev v, GBufDev gb, DevCounters *counters) {
-    __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
+    __shared__ uint32_t s_masks[kIsCompact<World> ? kSmemMaskMats * 16 : 1];
     World w = wa.w;
-    if constexpr (std::is_same<World, WorldCompact>::value) {
+    if constexpr (kIsCompact<World>) {
         stage_masks(s_masks, wa.masks, wa.n_mats);
         w.smem_masks = s_masks;
     }
@@ -223,6 +230,12 @@ __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) primary_kernel(World
     uint32_t is_hit = 0;
     float dx = 0.0f, dy = 0.0f, dz = 1.0f, sx = 0.0f, sy = 0.0f, sz = 0.0f;
     if (valid) primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
+    // traceMap's zero patch (map.glsl:85-90) applied here, remembering the patched components: the sky colour of a
+    // miss needs the unpatched direction, and one mask register is cheaper to keep alive than three floats
+    const uint32_t zmask = (dx == 0.0f ? 1u : 0u) | (dy == 0.0f ? 2u : 0u) | (dz == 0.0f ? 4u : 0u);
+    if (zmask & 1u) dx = 0.001f;
+    if (zmask & 2u) dy = 0.001f;
+    if (zmask & 4u) dz = 0.001f;
     Hit h;
     trace<World, COUNT>(w, valid, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);  // all 32 lanes
     if (valid) {
@@ -239,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) primary_kernel(World
             }
         } else {  // :63-68
             float r, g, b;
-            sky_dome2(dx, dy, dz, r, g, b);
+            sky_dome2((zmask & 1u) ? 0.0f : dx, (zmask & 2u) ? 0.0f : dy, (zmask & 4u) ? 0.0f : dz, r, g, b);
             gb.albedo[i] = pack_rgba8(r, g, b, 1.0f);
             gb.normal[i] = 0xFFFFFFFFu;
             gb.position[i] = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
@@ -278,9 +291,9 @@ __device__ __forceinline__ uint32_t shadow_pixel(const World &w, bool active, co
 // ---- secondary pass ------------------------------------------------------------------------
 template <class World, int COUNT>
 __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) secondary_kernel(WorldArgs<World> wa, ViewDev v, GBufDev gb, DevCounters *counters) {
-    __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
+    __shared__ uint32_t s_masks[kIsCompact<World> ? kSmemMaskMats * 16 : 1];
     World w = wa.w;
-    if constexpr (std::is_same<World, WorldCompact>::value) {
+    if constexpr (kIsCompact<World>) {
         stage_masks(s_masks, wa.masks, wa.n_mats);
         w.smem_masks = s_masks;
     }
@@ -360,9 +373,9 @@ __global__ void __launch_bounds__(256) shade_kernel(ViewDev v, GBufDev gb, Frame
 template <class World, bool GBUF, bool BATCH>
 __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS_FRAME) frame_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0, ViewDev v,
                                                          uint32_t shadow_steps, GBufDev gb, FrameTarget ft) {
-    __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
+    __shared__ uint32_t s_masks[kIsCompact<World> ? kSmemMaskMats * 16 : 1];
     World w = wa.w;
-    if constexpr (std::is_same<World, WorldCompact>::value) {
+    if constexpr (kIsCompact<World>) {
         stage_masks(s_masks, wa.masks, wa.n_mats);
         w.smem_masks = s_masks;
     }
@@ -372,6 +385,10 @@ __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS_FRAME) frame_kernel(W
     const CamDev &cam = BATCH ? cams[blockIdx.z] : cam0;
     float dx = 0.0f, dy = 0.0f, dz = 1.0f, sx = 0.0f, sy = 0.0f, sz = 0.0f;
     if (valid) primary_ray(cam, v, x, y, dx, dy, dz, sx, sy, sz);
+    const uint32_t zmask = (dx == 0.0f ? 1u : 0u) | (dy == 0.0f ? 2u : 0u) | (dz == 0.0f ? 4u : 0u);  // see primary_kernel
+    if (zmask & 1u) dx = 0.001f;
+    if (zmask & 2u) dy = 0.001f;
+    if (zmask & 4u) dz = 0.001f;
     Hit h;
     TripCounts tc;
     trace<World, 0>(w, valid, sx, sy, sz, dx, dy, dz, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);  // all 32 lanes
@@ -384,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS_FRAME) frame_kernel(W
         pos = make_float4(ceilf(h.hx) / 8.0f, ceilf(h.hy) / 8.0f, ceilf(h.hz) / 8.0f, 1.0f);
     } else {
         float r, g, b;
-        sky_dome2(dx, dy, dz, r, g, b);
+        sky_dome2((zmask & 1u) ? 0.0f : dx, (zmask & 2u) ? 0.0f : dy, (zmask & 4u) ? 0.0f : dz, r, g, b);
         albedo = pack_rgba8(r, g, b, 1.0f);
         normal = 0xFFFFFFFFu;
         pos = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
@@ -412,9 +429,9 @@ __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS_FRAME) frame_kernel(W
 // terrain_edit.comp.glsl:10-17: the centre pick ray (rayUV = 0)
 template <class World>
 __global__ void pick_kernel(WorldArgs<World> wa, CamDev cam, ViewDev v, uint8_t *out_hit) {
-    __shared__ uint32_t s_masks[std::is_same<World, WorldCompact>::value ? 256 * 16 : 1];
+    __shared__ uint32_t s_masks[kIsCompact<World> ? kSmemMaskMats * 16 : 1];
     World w = wa.w;
-    if constexpr (std::is_same<World, WorldCompact>::value) {
+    if constexpr (kIsCompact<World>) {
         stage_masks(s_masks, wa.masks, wa.n_mats);
         w.smem_masks = s_masks;
     }
@@ -639,6 +656,26 @@ __global__ void __launch_bounds__(512) clearance_kernel(const uint32_t *__restri
         if (found) { D = r; break; }
     }
     bricks8[addr] = (uint8_t)(kMatLimit + max(D - 2, 0));
+}
+
+// Dense block grid for the traversal kernels: dense[x + dim*(z + dim*y)] = the brick byte of block (x, y, z);
+// blocks of far-empty chunks get kMatLimit + min(n_free, 30) of their chunk.  One CTA per chunk, one thread per x-row.
+__global__ void __launch_bounds__(64) dense_fill_kernel(const uint32_t *__restrict__ chunks2, const uint8_t *__restrict__ bricks8,
+                                                        uint8_t *__restrict__ dense, int cd) {
+    const int cd1 = cd + 1;
+    const size_t cj = blockIdx.x;
+    const int cx = (int)(cj % cd), cy = (int)((cj / cd) % cd), cz = (int)(cj / ((size_t)cd * cd));
+    const int ly = threadIdx.x & 7, lz = threadIdx.x >> 3;
+    const uint32_t e = chunks2[(size_t)cx + (size_t)cd1 * ((size_t)cy + (size_t)cz * cd1)];
+    uint2 v;
+    if ((int)e < 0) {
+        const uint32_t b = kMatLimit + min(e & 0xFFu, 30u);
+        v.x = v.y = b * 0x01010101u;
+    } else {
+        v = *reinterpret_cast<const uint2 *>(bricks8 + (size_t)e * 512u + 8 * ly + 64 * lz);
+    }
+    const size_t dim = (size_t)cd * 8;
+    *reinterpret_cast<uint2 *>(dense + (size_t)cx * 8 + dim * ((size_t)(cz * 8 + lz) + dim * (size_t)(cy * 8 + ly))) = v;
 }
 
 // ---- bandwidth probes (roofline denominators) ----------------------------------

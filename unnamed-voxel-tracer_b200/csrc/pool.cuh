@@ -23,7 +23,7 @@ namespace uvt {
 
 constexpr int kPoolTile = 16;                 // CTA tile is kPoolTile x kPoolTile pixels
 constexpr int kPoolRays = kPoolTile * kPoolTile;
-constexpr int kPoolMaskMats = 64;             // sub-voxel masks of material ids < 64 live in shared memory
+constexpr int kPoolMaskMats = kSmemMaskMats;  // sub-voxel masks of material ids < 64 live in shared memory
 
 // flags word of a pooled ray
 constexpr uint32_t kFlagBig = 1u, kFlagMx = 2u, kFlagMy = 4u, kFlagClimbs = 8u, kFlagZeroShift = 4;  // bits 4-6: zero components of the unpatched direction

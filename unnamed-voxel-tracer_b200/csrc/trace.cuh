@@ -27,6 +27,8 @@ struct Hit {
     uint32_t exit_kind;  // 0 hit, 1 cap, 2 left the map
 };
 
+constexpr int kSmemMaskMats = 64;  // sub-voxel masks of material ids < 64 are staged in shared memory, the rest read through L1
+
 struct TripCounts {
     uint32_t t_in, t_chunk, t_block;
 };
@@ -75,12 +77,15 @@ struct WorldCompact {
     const uint8_t *__restrict__ bricks8;    // [n_bricks][512], value = material id (0 = empty)
     const uint32_t *__restrict__ mat_word;  // [256] material id -> block word
     const uint32_t *__restrict__ mat_color; // [256][512] material id -> model texels
-    const uint32_t *smem_masks;             // [256][16] shared-memory copy of the occupancy masks
+    const uint32_t *smem_masks;             // [kSmemMaskMats][16] shared-memory copy of the first occupancy masks
+    const uint32_t *__restrict__ g_masks;   // [256][16] all occupancy masks (global)
     uint32_t cd;
     uint32_t cd1;                           // cd + 1: stride of chunks2 (one guard layer on the high side)
     uint32_t n_real_bricks;                 // bricks [0, n_real) mirror reference bricks; the rest only carry clearances
     int32_t y_clear;                        // every block with y >= y_clear is empty (max occupied block y + 1)
     int32_t dim;                            // MAP_DIMENSION in blocks
+    const uint8_t *__restrict__ dense;      // [dim^3] one byte per block, x + dim*(z + dim*y): the brick bytes (far-empty chunks:
+                                            // kMatLimit + min(n_free, 30)) without the chunk indirection; nullptr when not built
     const uint16_t *__restrict__ clear4;    // [(dim/4)^2] per 4x4-block column group, grown by one block on every side:
                                             // every block with y >= clear4 there is empty (sky_sealed)
 
@@ -96,13 +101,23 @@ struct WorldCompact {
     }
     __device__ __forceinline__ bool sub_solid(uint32_t mat, uint32_t px, uint32_t py, uint32_t pz, uint32_t &color) const {
         const uint32_t bit = (px & 7u) + ((py & 7u) << 3) + ((pz & 7u) << 6);
-        const uint32_t word = smem_masks[mat * 16u + (bit >> 5)];
+        const uint32_t word = mask_word(mat, bit);
         if (((word >> (bit & 31u)) & 1u) == 0) return false;
         color = __ldg(&mat_color[mat * 512u + bit]);
         return true;
     }
     __device__ __forceinline__ uint32_t block_word(uint32_t mat) const { return __ldg(&mat_word[mat]); }
+    __device__ __forceinline__ uint32_t mask_word(uint32_t mat, uint32_t bit) const {
+        return mat < (uint32_t)kSmemMaskMats ? smem_masks[mat * 16u + (bit >> 5)] : __ldg(&g_masks[mat * 16u + (bit >> 5)]);
+    }
 };
+
+// Same data; selects (at compile time) the traversal that reads the dense block grid instead of
+// chunk table + bricks.
+struct WorldDense : WorldCompact {};
+
+template <class World>
+constexpr bool kIsCompact = std::is_same<World, WorldCompact>::value || std::is_same<World, WorldDense>::value;
 
 // ---- traceMap ------------------------------------------------------------------------
 // map.glsl:83-168.  `bound` = 8 * MAP_DIMENSION.
@@ -356,7 +371,7 @@ constexpr uint32_t kMatLimit = 224;  // brick bytes >= kMatLimit encode empty bl
 constexpr int kDead = 0x40000000;    // `limit` of a lane without a live ray
 
 // Must be called by ALL 32 lanes of a warp (it uses full-mask warp reductions); `active` = this lane has a ray.
-template <int COUNT>
+template <int COUNT, bool DENSE>
 __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool active, float ox, float oy, float oz, float dx, float dy, float dz,
                                                int max_steps, int bound, Hit &out, TripCounts &tc) {
     if (dx == 0.0f) dx = 0.001f;
@@ -435,28 +450,52 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
                 limit = kDead;
             } else {
                 if (COUNT == 2) tc.t_in++;  // lookups performed
-                const uint32_t px = (uint32_t)gx + __float2uint_rz(wx);
-                const uint32_t py = (uint32_t)gy + __float2uint_rz(wy);
-                const uint32_t pz = (uint32_t)gz + __float2uint_rz(wz);
+                uint32_t px = (uint32_t)gx, py = (uint32_t)gy, pz = (uint32_t)gz;
                 uint32_t mat;
                 int n_free = 0;
-                // out.p* hold the `pos` of the previous lookup: still inside that (non-empty) block?
-                if (!big && cmat != 0u && (((px ^ out.px) | (py ^ out.py) | (pz ^ out.pz)) < 8u)) {
-                    mat = cmat;
-                    if (COUNT == 1) tc.t_chunk++;
-                } else {
-                    const uint32_t e = __ldg(&w.chunks2[(px >> 6) + cd1 * ((py >> 6) + (pz >> 6) * cd1)]);
-                    if ((int)e < 0) {
-                        n_free = (int)(e & 0xFFu);
-                        mat = 0u;
-                    } else {
-                        if (COUNT == 1 && e < w.n_real_bricks) tc.t_chunk++;
-                        const uint32_t b8 = __ldg(&w.bricks8[e * 512u + (((px >> 3) & 7u) | (py & 0x38u) | ((pz & 0x38u) << 3))]);
-                        const bool is_mat = b8 < kMatLimit;
-                        n_free = is_mat ? 0 : (int)(b8 - kMatLimit);
-                        mat = is_mat ? b8 : 0u;
+                if (DENSE && COUNT != 1) {
+                    // dense block grid: at block steps with within < 8 the block of `pos` is g >> 3, so the
+                    // float->int conversions of map.glsl:108 are only needed for sub-voxel steps / round-up carries
+                    const bool exact = !big || fmaxf(fmaxf(wx, wy), wz) >= 8.0f;
+                    uint32_t b8 = kMatLimit;  // `pos` one block past the high map face: empty, nothing known
+                    const uint32_t udim = (uint32_t)w.dim;
+                    if (exact) {
+                        px += __float2uint_rz(wx);
+                        py += __float2uint_rz(wy);
+                        pz += __float2uint_rz(wz);
                     }
-                    cmat = mat;
+                    if (!exact || ((px >> 3) < udim && (py >> 3) < udim && (pz >> 3) < udim))
+                        b8 = __ldg(&w.dense[(size_t)(px >> 3) + (size_t)udim * ((pz >> 3) + udim * (py >> 3))]);
+                    const bool is_mat = b8 < kMatLimit;
+                    n_free = is_mat ? 0 : (int)(b8 - kMatLimit);
+                    mat = is_mat ? b8 : 0u;
+                    if (is_mat && !exact) {  // the sub-voxel test needs the exact `pos`
+                        px += __float2uint_rz(wx);
+                        py += __float2uint_rz(wy);
+                        pz += __float2uint_rz(wz);
+                    }
+                } else {
+                    px += __float2uint_rz(wx);
+                    py += __float2uint_rz(wy);
+                    pz += __float2uint_rz(wz);
+                    // out.p* hold the `pos` of the previous lookup: still inside that (non-empty) block?
+                    if (!big && cmat != 0u && (((px ^ out.px) | (py ^ out.py) | (pz ^ out.pz)) < 8u)) {
+                        mat = cmat;
+                        if (COUNT == 1) tc.t_chunk++;
+                    } else {
+                        const uint32_t e = __ldg(&w.chunks2[(px >> 6) + cd1 * ((py >> 6) + (pz >> 6) * cd1)]);
+                        if ((int)e < 0) {
+                            n_free = (int)(e & 0xFFu);
+                            mat = 0u;
+                        } else {
+                            if (COUNT == 1 && e < w.n_real_bricks) tc.t_chunk++;
+                            const uint32_t b8 = __ldg(&w.bricks8[e * 512u + (((px >> 3) & 7u) | (py & 0x38u) | ((pz & 0x38u) << 3))]);
+                            const bool is_mat = b8 < kMatLimit;
+                            n_free = is_mat ? 0 : (int)(b8 - kMatLimit);
+                            mat = is_mat ? b8 : 0u;
+                        }
+                        cmat = mat;
+                    }
                 }
                 out.px = px; out.py = py; out.pz = pz;
                 if (COUNT == 1) n_free = 0;  // exact reference counters need every lookup
@@ -471,7 +510,7 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
                 } else if (mat != 0u) {  // a block: test the sub-voxel
                     if (COUNT == 1) tc.t_block++;
                     const uint32_t bit = (px & 7u) | ((py & 7u) << 3) | ((pz & 7u) << 6);
-                    const uint32_t word = w.smem_masks[mat * 16u + (bit >> 5)];
+                    const uint32_t word = w.mask_word(mat, bit);
                     if ((word >> (bit & 31u)) & 1u) {
                         out.data = __ldg(&w.mat_color[mat * 512u + bit]);
                         out.face = mx ? (posx ? 1u : 2u) : (my ? (posy ? 3u : 4u) : (posz ? 5u : 6u));
@@ -540,7 +579,7 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
 template <class World, int COUNT>
 __device__ __forceinline__ void trace(const World &w, bool active, float ox, float oy, float oz, float dx, float dy, float dz,
                                       int max_steps, int bound, Hit &out, TripCounts &tc) {
-    if constexpr (std::is_same<World, WorldCompact>::value) trace_map_fast<COUNT>(w, active, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
+    if constexpr (kIsCompact<World>) trace_map_fast<COUNT, std::is_same<World, WorldDense>::value>(w, active, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
     else if (active) {
         trace_map<World, COUNT == 1>(w, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
         if (COUNT == 2) tc.t_in = tc.t_chunk = tc.t_block = 0;

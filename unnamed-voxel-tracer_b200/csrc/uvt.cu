@@ -52,6 +52,8 @@ struct uvt_ctx {
     size_t n_total_bricks = 0;      // real + virtual (clearance-only) bricks in d_bricks8
     int32_t y_clear = 0;            // max occupied block y + 1 (every block at or above is empty)
     uint16_t *d_clear4 = nullptr;   // [(dim/4)^2] dilated column-group tops for sky_sealed()
+    uint8_t *d_dense = nullptr;     // [dim^3] dense block grid (nullptr: not built — too large or disabled)
+    bool dense_valid = false;
     bool world_committed = false;
 
     // ---- atlas: host copy by slot (slot = x/8 + 32*(y/8) + 1024*(z/8)), device [n_slots][512]
@@ -247,10 +249,12 @@ WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     a.w.y_clear = c->y_clear;
     a.w.dim = (int32_t)c->dim;
     a.w.clear4 = c->d_clear4;
+    a.w.dense = c->d_dense;
     a.w.bricks8 = c->d_bricks8;
     a.w.mat_word = c->d_mat_word;
     a.w.mat_color = c->d_mat_color;
     a.w.smem_masks = nullptr;
+    a.w.g_masks = c->d_mat_mask;
     a.w.cd = c->cd;
     a.masks = c->d_mat_mask;
     a.n_mats = (uint32_t)(c->mat_words.size() - 1);
@@ -326,6 +330,17 @@ void launch_primary_world(uvt_ctx *c, const WorldArgs<World> &wa, const ViewDev 
 #undef UVT_LAUNCH
 }
 
+bool use_dense(const uvt_ctx *c) { return use_compact(c) && c->dense_valid && !(c->params.flags & UVT_FLAG_NO_DENSE); }
+
+WorldArgs<WorldDense> world_dense(const uvt_ctx *c) {
+    const WorldArgs<WorldCompact> s = world_compact(c);
+    WorldArgs<WorldDense> a;
+    static_cast<WorldCompact &>(a.w) = s.w;
+    a.masks = s.masks;
+    a.n_mats = s.n_mats;
+    return a;
+}
+
 bool use_pool(const uvt_ctx *c) { return use_compact(c) && c->params.scheduler == UVT_SCHED_POOL; }
 
 dim3 pool_grid(const uvt_ctx *c) {
@@ -350,6 +365,7 @@ int launch_primary(uvt_ctx *c) {
     const GBufDev g = make_gbuf(c);
     const dim3 grid = trace_grid(c);
     if (use_pool(c)) launch_primary_pool<COUNT>(c, v, g);
+    else if (COUNT != 1 && use_dense(c)) launch_primary_world<WorldDense, COUNT>(c, world_dense(c), v, g, grid);  // exact counters read the bricks
     else if (use_compact(c)) launch_primary_world<WorldCompact, COUNT>(c, world_compact(c), v, g, grid);
     else launch_primary_world<WorldRef, COUNT>(c, world_ref(c), v, g, grid);
     return check_launch(c, "primary_kernel");
@@ -361,6 +377,7 @@ int launch_secondary(uvt_ctx *c) {
     const GBufDev g = make_gbuf(c);
     const dim3 grid = trace_grid(c);
     if (use_pool(c)) secondary_pool_kernel<COUNT><<<pool_grid(c), kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
+    else if (COUNT != 1 && use_dense(c)) secondary_kernel<WorldDense, COUNT><<<grid, kThreads, 0, c->stream>>>(world_dense(c), v, g, c->d_counters);
     else if (use_compact(c)) secondary_kernel<WorldCompact, COUNT><<<grid, kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
     else secondary_kernel<WorldRef, COUNT><<<grid, kThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
     return check_launch(c, "secondary_kernel");
@@ -454,6 +471,21 @@ int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
         clearance_kernel<<<(unsigned)n_total, 512, 0, c->stream>>>(c->d_chunks2, cd, brick_chunk, rowmask, c->d_bricks8);
         c->launches += 2;
     }
+    // dense block grid (skipped when dim^3 bytes do not fit comfortably: the brick path is used instead)
+    c->dense_valid = false;
+    {
+        const size_t bytes = (size_t)c->dim * c->dim * c->dim;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (!c->d_dense && bytes <= (size_t)16 << 30 && bytes * 2 < free_b) {
+            if (cudaMalloc(&c->d_dense, bytes) != cudaSuccess) { c->d_dense = nullptr; (void)cudaGetLastError(); }
+        }
+        if (c->d_dense) {
+            dense_fill_kernel<<<(unsigned)n_chunks, 64, 0, c->stream>>>(c->d_chunks2, c->d_bricks8, c->d_dense, cd);
+            c->launches++;
+            c->dense_valid = true;
+        }
+    }
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     cleanup();
@@ -476,7 +508,7 @@ void uvt_default_params(uvt_params *p) {
     p->epsilon = 0.001f;
     p->flags = UVT_FLAG_ENTITIES;
     p->layout = UVT_LAYOUT_COMPACT;
-    p->scheduler = UVT_SCHED_POOL;
+    p->scheduler = UVT_SCHED_TILE;
 }
 
 int uvt_abi_version(void) { return UVT_ABI_VERSION; }
@@ -530,7 +562,7 @@ void uvt_destroy(uvt_ctx *c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     free_gbuffer(c);
     cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
-    cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4);
+    cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
     cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame);
     for (int i = 0; i < 4; ++i)
@@ -625,7 +657,9 @@ int uvt_world_alloc(uvt_ctx *c, uint32_t dim, uint32_t **chunks_host, uint32_t *
     UVT_REQUIRE(c, brick_capacity > 0, "brick_capacity must be > 0");
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
-    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4);
+    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
+    c->d_dense = nullptr;
+    c->dense_valid = false;
     c->h_chunks = c->h_bricks = nullptr;
     c->d_chunks = nullptr;
     c->d_chunks2 = nullptr;
@@ -851,7 +885,7 @@ int uvt_dispatch_frame(uvt_ctx *c) {
     const dim3 grid = trace_grid(c);
     const CamDev *cams = c->layers > 1 ? c->d_cams : nullptr;
     PassTimer t(c, 3);
-    if (use_pool(c)) {
+    if (use_pool(c) || (c->params.flags & UVT_FLAG_SPLIT_FRAME)) {
         // pooled scheduler: the three passes of game.zig:244-255 as three launches (the G-buffer round trip through
         // L2 costs far less than the lanes a fused pixel-per-thread kernel leaves idle)
         rc = launch_primary<0>(c);
@@ -864,7 +898,10 @@ int uvt_dispatch_frame(uvt_ctx *c) {
     const bool batch = c->layers > 1;
     const uint32_t ss = c->params.shadow_max_steps;
     const FrameTarget ft = make_target(c);
-    if (use_compact(c)) {
+    if (use_dense(c)) {
+        if (batch) frame_kernel<WorldDense, true, true><<<grid, kThreads, 0, c->stream>>>(world_dense(c), cams, c->cam0, v, ss, g, ft);
+        else frame_kernel<WorldDense, true, false><<<grid, kThreads, 0, c->stream>>>(world_dense(c), cams, c->cam0, v, ss, g, ft);
+    } else if (use_compact(c)) {
         if (batch) frame_kernel<WorldCompact, true, true><<<grid, kThreads, 0, c->stream>>>(world_compact(c), cams, c->cam0, v, ss, g, ft);
         else frame_kernel<WorldCompact, true, false><<<grid, kThreads, 0, c->stream>>>(world_compact(c), cams, c->cam0, v, ss, g, ft);
     } else {
