@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--scheduler", default="tile", choices=["pool", "tile"],
                     help="tile = one pixel per thread (default); pool = per-CTA ray pool compacted between trip phases")
     ap.add_argument("--no-dense", action="store_true", help="traverse through chunk table + bricks instead of the dense block grid")
-    ap.add_argument("--split-frame", action="store_true", help="frame = primary + secondary + shade launches instead of the fused kernel")
+    ap.add_argument("--fused-frame", action="store_true", help="frame = ONE fused kernel instead of the default primary + secondary + shade launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed steps (reported in config)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
@@ -206,7 +206,7 @@ def run_ours(args):
     dim, W, H, shadows, desc = WORKLOADS[args.workload]
     models = load_models()
 
-    ctx = uvt.Context(local_rank, map_dim=dim, layout=args.layout, dense=not args.no_dense, split_frame=args.split_frame)
+    ctx = uvt.Context(local_rank, map_dim=dim, layout=args.layout, dense=not args.no_dense, fused_frame=args.fused_frame)
     ctx.set_scheduler(args.scheduler)
     stream = torch.cuda.Stream(device=local_rank)
     ctx.set_stream(stream.cuda_stream)  # launch on a torch stream so torch.cuda events / NCCL ordering see the work
@@ -324,6 +324,11 @@ def run_ours(args):
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop()
 
+    pass_ms = None
+    if shadows:  # per-pass device time of one frame (outside the timed region)
+        ctx.dispatch_primary(); ctx.dispatch_secondary(); ctx.shade(); ctx.sync()
+        pass_ms = {k: ctx.last_pass_ms(k) for k in ("primary", "secondary", "shade")}
+
     verified = None
     if p2p:
         # the peer-stored frame must equal the NCCL-gathered one (checked outside the timed region)
@@ -414,6 +419,8 @@ def run_ours(args):
                             "peak_source": "measured in this run: 16-B ld.global.cg reads of a 32 MiB L2-resident buffer"},
             "wall_ms_per_step": wall / args.steps * 1e3,
         }
+        if pass_ms:
+            line["pass_ms"] = pass_ms
         if tiled:
             line["gather_ms"] = float(np.mean(gather_ms)) if gather_ms else 0.0
             line["config"]["gather"] = ("p2p: kernels store bands into rank 0's frame over NVLink (CUDA IPC peer mapping), no collective"

@@ -54,7 +54,7 @@ enum {
     UVT_FLAG_HIT_BUFFER = 1u << 0, /* also write the explicit hit buffer (uvt_hit) in the primary pass */
     UVT_FLAG_ENTITIES   = 1u << 1, /* shadow pass runs traceEntities (map.glsl:172-201); on by default */
     UVT_FLAG_NO_DENSE   = 1u << 2, /* do not use the dense block grid (dim^3 bytes); traverse through chunk table + bricks */
-    UVT_FLAG_SPLIT_FRAME = 1u << 3 /* uvt_dispatch_frame issues the three passes as three launches instead of the fused kernel */
+    UVT_FLAG_FUSED_FRAME = 1u << 3 /* uvt_dispatch_frame runs ONE fused kernel instead of the (faster, default) three launches */
 };
 
 typedef enum uvt_layout {

@@ -103,7 +103,7 @@ def test_committed_golden_fixture(uvt, oracle, w1):
         assert channel_diff(g["frame"], gold["frame"]).max() <= 1
 
 
-def test_fused_frame_equals_three_passes(uvt, oracle, w1):
+def test_dispatch_frame_equals_three_passes(uvt, oracle, w1):
     ctx, sc = w1
     ctx.set_layout("compact")
     ctx.resize(640, 360)
@@ -113,6 +113,32 @@ def test_fused_frame_equals_three_passes(uvt, oracle, w1):
     for k in ("albedo", "normal", "illumination", "frame"):
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(a["position"].view(np.uint32), b["position"].view(np.uint32))
+
+
+@pytest.mark.parametrize("variant", ["bricks", "pool", "pool-bricks", "fused", "fused-bricks"])
+def test_every_kernel_variant_matches_the_oracle(uvt, oracle, scene_factory, variant):
+    """The traversal exists in several instantiations (dense block grid / chunk table + bricks; pixel-per-thread /
+    pooled scheduler; three launches / fused frame kernel).  The default (dense, tile, three launches) is what every
+    other test runs; here each alternative is held to the same bit-exact bar."""
+    kw = dict(hit_buffer=True, dense="bricks" not in variant, fused_frame=variant.startswith("fused"))
+    with uvt.Context(0, **kw) as ctx:
+        sc = scene_factory(512, "procgen", ctx=ctx)
+        ctx.set_scheduler("pool" if variant.startswith("pool") else "tile")
+        for cam, size in ((camera_k1(uvt, oracle), (320, 180)), (camera_k0(oracle), (250, 130))):
+            ctx.resize(*size)
+            g = gpu_render(ctx, cam, three_pass=not variant.startswith("fused"))
+            r = oracle.render(sc.oracle_world, cam, *size)
+            if variant.startswith("fused"):  # the fused kernel does not write the explicit hit buffer: G-buffer parity
+                hit = r["hits"]["face"] != 0
+                assert np.array_equal(g["normal"], r["normal"])
+                assert np.array_equal(g["position"].view(np.uint32), r["position"].view(np.uint32))
+                assert np.array_equal(g["albedo"][hit], r["albedo"][hit]) and channel_diff(g["albedo"], r["albedo"]).max() <= 1
+            else:
+                assert_primary_parity(g, r)
+            assert np.array_equal(g["illumination"], r["illumination"])
+            assert channel_diff(g["frame"], r["frame"]).max() <= 1
+            assert ctx.count_pass("primary") == r["primary_counters"]
+            assert ctx.count_pass("secondary") == r["secondary_counters"]
 
 
 @pytest.mark.parametrize("size", [(1, 1), (17, 9), (33, 31), (250, 130)])

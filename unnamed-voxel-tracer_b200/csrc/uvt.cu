@@ -885,9 +885,10 @@ int uvt_dispatch_frame(uvt_ctx *c) {
     const dim3 grid = trace_grid(c);
     const CamDev *cams = c->layers > 1 ? c->d_cams : nullptr;
     PassTimer t(c, 3);
-    if (use_pool(c) || (c->params.flags & UVT_FLAG_SPLIT_FRAME)) {
-        // pooled scheduler: the three passes of game.zig:244-255 as three launches (the G-buffer round trip through
-        // L2 costs far less than the lanes a fused pixel-per-thread kernel leaves idle)
+    if (use_pool(c) || !(c->params.flags & UVT_FLAG_FUSED_FRAME)) {
+        // the three passes of game.zig:244-255 as three launches: measured faster than the fused kernel (c1 0.301 vs
+        // 0.324 ms, c3 2.21 vs 2.41 ms) — the G-buffer round trip through L2 costs less than the registers and the
+        // idle lanes of a kernel that keeps a primary and a shadow ray's state alive at once
         rc = launch_primary<0>(c);
         if (rc == UVT_OK) rc = launch_secondary<0>(c);
         if (rc != UVT_OK) return rc;

@@ -41,7 +41,7 @@ class Context:
     """gfx.init (graphics.zig:60-75): one CUDA device + one in-order stream."""
 
     def __init__(self, device=0, *, map_dim=512, primary_max_steps=192, shadow_max_steps=48, hit_buffer=False,
-                 entities=True, layout="compact", dense=True, split_frame=False):
+                 entities=True, layout="compact", dense=True, fused_frame=False):
         L = N.load()
         p = N.Params()
         L.uvt_default_params(ctypes.byref(p))
@@ -49,7 +49,7 @@ class Context:
         p.primary_max_steps = primary_max_steps
         p.shadow_max_steps = shadow_max_steps
         p.flags = ((N.UVT_FLAG_HIT_BUFFER if hit_buffer else 0) | (N.UVT_FLAG_ENTITIES if entities else 0) |
-                   (0 if dense else N.UVT_FLAG_NO_DENSE) | (N.UVT_FLAG_SPLIT_FRAME if split_frame else 0))
+                   (0 if dense else N.UVT_FLAG_NO_DENSE) | (N.UVT_FLAG_FUSED_FRAME if fused_frame else 0))
         p.layout = N.UVT_LAYOUT_COMPACT if layout == "compact" else N.UVT_LAYOUT_REFERENCE
         h = ctypes.c_void_p()
         rc = L.uvt_create(ctypes.byref(p), int(device), ctypes.byref(h))
