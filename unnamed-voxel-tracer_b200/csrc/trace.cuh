@@ -420,29 +420,37 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
     int trip = 0;                     // warp-uniform
     int limit = fast ? 0 : kDead;     // trips in [trip, limit) need no lookup; kDead parks the lane
     bool mx = true, my = false;       // minIdx of the previous trip == 0 / == 1 (starts at 0, map.glsl:98)
-    int next_try = 4;                 // warp-uniform: next trip at which climbing lanes try sky_sealed()
+    // warp-uniform: DDA runs stop at the segment ends 4, 32, 64, 128, ... (4, 12, 28 for the 48-trip shadow cap), where the
+    // climbing lanes try sky_sealed() together.  Measured on the default world, 63 % of the sky rays pass at trip 4 and most
+    // of the rest at 32 / 64 / 128; a failed test is cheap.
+    int seg_end = min(4, max_steps);
 
     uint32_t cmat = 0;  // material of the block looked up last (0: none) — sub-voxel steps mostly stay inside it
 
     for (;;) {
-        // ---- sealed-ray test (c), all candidate lanes of the warp at once ------------------
-        if (trip >= next_try) {
-            // tried at trips 4, 32, 64, 128 (long caps) or 4, 12, 28 (the 48-trip shadow cap): measured on the default
-            // world, 63 % of the sky rays pass at trip 4 and most of the rest at 32 / 64 / 128; a failed test is cheap
-            next_try = max_steps > 64 ? (next_try == 4 ? 32 : 2 * next_try) : 2 * next_try + 4;
-            if (climbs && limit < kDead && big &&
-                sky_sealed(w.clear4, w.dim, w.y_clear, ((float)gx + wx) * 0.125f, ((float)gy + wy) * 0.125f, ((float)gz + wz) * 0.125f, dx, dy, dz, max_steps - trip)) {
-                out.trips = (uint32_t)max_steps;  // iteration-cap miss (map.glsl:167)
-                out.px = out.py = out.pz = 0xFFFFFFFFu;
-                limit = kDead;
-            }
-        }
-
         // ---- lookups (map.glsl:107-144) --------------------------------------------------
         // A round is paid for by the whole warp, so EVERY live lane looks up, not only the ones whose
         // free trips ran out: a lane still inside its free run re-reads an (empty) block and refreshes
         // its clearance from the new position, which keeps the lanes' lookups aligned (fewer rounds).
-        if (limit < kDead) {
+        bool slow = limit < kDead;
+        if (DENSE && COUNT != 1 && slow) {
+            // the common lookup, kept short: a block step (no round-up carry) inside the map that finds an empty block and
+            // does not seal the ray.  Anything else falls through to the general code below, which redoes the lookup.
+            const uint32_t gmax = max(max((uint32_t)gx, (uint32_t)gy), (uint32_t)gz);
+            const bool inside = gmax < (uint32_t)bound;
+            const uint32_t udim = (uint32_t)w.dim;
+            uint32_t code = 0;
+            if (inside) code = __ldg(&w.dense[(size_t)((uint32_t)gx >> 3) + (size_t)udim * (((uint32_t)gz >> 3) + udim * ((uint32_t)gy >> 3))]);
+            const int lim0 = max(limit, trip + 1 + (int)code - (int)kMatLimit);
+            const bool simple = big && code >= kMatLimit && fmaxf(fmaxf(wx, wy), wz) < 8.0f;
+            const bool seals = lim0 >= max_steps || (climbs && (gy >> 3) >= w.y_clear);
+            if (simple && !seals) {
+                limit = lim0;
+                slow = false;
+                if (COUNT == 2) tc.t_in++;
+            }
+        }
+        if (slow) {
             if ((unsigned)gx >= (unsigned)bound || (unsigned)gy >= (unsigned)bound || (unsigned)gz >= (unsigned)bound) {
                 out.exit_kind = 2;
                 out.trips = (uint32_t)trip;
@@ -550,8 +558,9 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
 
         // ---- how many trips can the whole warp run without a lookup? ----------------------
         // live lanes: 1 <= limit - trip (limit is clamped to max_steps > trip); parked lanes: huge
-        const int k = __reduce_min_sync(0xFFFFFFFFu, limit - trip);
+        int k = __reduce_min_sync(0xFFFFFFFFu, limit - trip);
         if (k >= kDead / 2) break;  // no live lane left
+        k = min(k, seg_end - trip);  // warp-uniform; >= 1
 
         // ---- k DDA steps, branch-free (map.glsl:157-162) -----------------------------------
         for (int j = 1; j < k; ++j) dda_step(gx, gy, gz, wx, wy, wz, isx, isy, isz, tgx, tgy, tgz, invx, invy, invz, dx, dy, dz, rsx, rsy, rsz);
@@ -562,12 +571,22 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
             my = myi != 0;
         }
         trip += k;
-        if (trip >= max_steps) {  // iteration cap: miss (map.glsl:167); in lockstep it ends every live lane at once
-            if (limit < kDead) {
-                out.trips = (uint32_t)trip;
-                out.px = out.py = out.pz = 0xFFFFFFFFu;
+        if (trip == seg_end) {  // warp-uniform
+            if (trip >= max_steps) {  // iteration cap: miss (map.glsl:167); in lockstep it ends every live lane at once
+                if (limit < kDead) {
+                    out.trips = (uint32_t)trip;
+                    out.px = out.py = out.pz = 0xFFFFFFFFu;
+                }
+                break;
             }
-            break;
+            seg_end = min(max_steps > 64 ? (seg_end == 4 ? 32 : 2 * seg_end) : 2 * seg_end + 4, max_steps);
+            // ---- sealed-ray test (c), all candidate lanes of the warp at once ----------------
+            if (climbs && limit < kDead && big &&
+                sky_sealed(w.clear4, w.dim, w.y_clear, ((float)gx + wx) * 0.125f, ((float)gy + wy) * 0.125f, ((float)gz + wz) * 0.125f, dx, dy, dz, max_steps - trip)) {
+                out.trips = (uint32_t)max_steps;  // iteration-cap miss (map.glsl:167)
+                out.px = out.py = out.pz = 0xFFFFFFFFu;
+                limit = kDead;
+            }
         }
     }
     if (COUNT == 1 && fast) tc.t_in = out.trips;  // every executed trip passed the bounds test
