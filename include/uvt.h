@@ -188,6 +188,12 @@ typedef enum uvt_buffer_kind {
 /* Row 0 is the BOTTOM image row (GL image origin). Copies layer 0..n_layers-1 back to back. */
 int  uvt_readback(uvt_ctx *ctx, uvt_buffer_kind kind, void *dst, size_t bytes);
 size_t uvt_buffer_bytes(uvt_ctx *ctx, uvt_buffer_kind kind);
+/* Pipelined readback (what a presenting loop does instead of a blocking glReadPixels): the buffer is snapshotted on the
+ * ctx stream (device-to-device, so the next dispatch may overwrite it at once) and copied to `dst` (pinned host memory
+ * from uvt_alloc_pinned) on a separate copy stream while the next frame renders.  At most two readbacks are in flight;
+ * a third call first waits for the oldest.  uvt_readback_wait() returns when every outstanding copy has landed. */
+int  uvt_readback_async(uvt_ctx *ctx, uvt_buffer_kind kind, void *dst, size_t bytes);
+int  uvt_readback_wait(uvt_ctx *ctx);
 /* Device address of a buffer (for NCCL / peer access by the caller's communication layer). */
 int  uvt_device_ptr(uvt_ctx *ctx, uvt_buffer_kind kind, void **dptr);
 /* Redirect the FRAME output to caller-owned device memory (may be a peer-mapped

@@ -450,3 +450,22 @@ def test_fast_path_fetches_fewer_trips(uvt, oracle, w1):
     stats = ctx.fetch_stats("primary")
     assert stats["rays"] == exact["rays"] == 320 * 180 and stats["hits"] == exact["hits"]
     assert stats["lookups"] < 0.6 * exact["t_in"]
+
+
+def test_pipelined_readback_matches_blocking(uvt, oracle, w1):
+    """uvt_readback_async snapshots the buffer on the ctx stream, so the next dispatch may overwrite it at once."""
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    ctx.resize(320, 180)
+    cams = [camera_k0(oracle), camera_k1(uvt, oracle), oracle.make_camera((300.0, 40.0, 200.0), pitch_yaw_matrix(uvt, 0.3, 4.0))]
+    expect = []
+    for cam in cams:
+        ctx.set_camera(cam); ctx.dispatch_primary()
+        expect.append(ctx.readback("albedo").copy())
+    bufs = [ctx.pinned_empty(320 * 180 * 4, np.uint32) for _ in cams]
+    for cam, buf in zip(cams, bufs):          # three frames in flight through two snapshot slots
+        ctx.set_camera(cam); ctx.dispatch_primary()
+        ctx.readback_async("albedo", buf)
+    ctx.readback_wait()
+    for buf, e in zip(bufs, expect):
+        assert np.array_equal(buf.reshape(180, 320), e)

@@ -89,6 +89,14 @@ struct uvt_ctx {
     bool frame_target_global_rows = false;
     void *shared_frame = nullptr;  // owned full-frame allocation exported over CUDA IPC (presenting rank)
 
+    // ---- pipelined readback: two device snapshots + a copy stream
+    cudaStream_t copy_stream = nullptr;
+    void *snap[2] = {nullptr, nullptr};
+    size_t snap_bytes[2] = {0, 0};
+    cudaEvent_t snap_ready[2] = {}, snap_done[2] = {};
+    bool snap_busy[2] = {false, false};
+    int snap_next = 0;
+
     // ---- counters / timing
     DevCounters *d_counters = nullptr;
     uint8_t *d_pick = nullptr;
@@ -545,6 +553,11 @@ int uvt_create(const uvt_params *params, int device, uvt_ctx **out) {
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 2; ++j)
             if ((e = cudaEventCreate(&c->ev[i][j])) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate (copy)");
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaEventCreateWithFlags(&c->snap_ready[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+        if ((e = cudaEventCreateWithFlags(&c->snap_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    }
     if ((e = cudaMalloc(&c->d_counters, sizeof(DevCounters))) != cudaSuccess) return fail(e, "cudaMalloc counters");
     if ((e = cudaMalloc(&c->d_pick, 32)) != cudaSuccess) return fail(e, "cudaMalloc pick");
     if ((e = cudaMalloc(&c->d_sink, 4)) != cudaSuccess) return fail(e, "cudaMalloc sink");
@@ -560,6 +573,12 @@ void uvt_destroy(uvt_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->snap[i]);
+        if (c->snap_ready[i]) cudaEventDestroy(c->snap_ready[i]);
+        if (c->snap_done[i]) cudaEventDestroy(c->snap_done[i]);
+    }
     free_gbuffer(c);
     cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
     cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
@@ -964,6 +983,45 @@ int uvt_readback(uvt_ctx *c, uvt_buffer_kind kind, void *dst, size_t bytes) {
     UVT_REQUIRE(c, bytes <= c->gbuf_pixels * bpp, "readback larger than the buffer");
     UVT_CUDA(c, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, c->stream));
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return UVT_OK;
+}
+
+int uvt_readback_async(uvt_ctx *c, uvt_buffer_kind kind, void *dst, size_t bytes) {
+    if (!c || !dst) return UVT_ERR_INVALID;
+    void *p = nullptr;
+    size_t bpp = 0;
+    int rc = buffer_info(c, kind, &p, &bpp);
+    if (rc != UVT_OK) return rc;
+    UVT_REQUIRE(c, bytes <= c->gbuf_pixels * bpp, "readback larger than the buffer");
+    const int s = c->snap_next;
+    c->snap_next ^= 1;
+    if (c->snap_busy[s]) {  // the snapshot slot is reused: its previous copy must have landed
+        UVT_CUDA(c, cudaEventSynchronize(c->snap_done[s]));
+        c->snap_busy[s] = false;
+    }
+    if (c->snap_bytes[s] < bytes) {
+        cudaFree(c->snap[s]);
+        c->snap[s] = nullptr;
+        c->snap_bytes[s] = 0;
+        UVT_CUDA(c, cudaMalloc(&c->snap[s], bytes));
+        c->snap_bytes[s] = bytes;
+    }
+    UVT_CUDA(c, cudaMemcpyAsync(c->snap[s], p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    UVT_CUDA(c, cudaEventRecord(c->snap_ready[s], c->stream));
+    UVT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->snap_ready[s], 0));
+    UVT_CUDA(c, cudaMemcpyAsync(dst, c->snap[s], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    UVT_CUDA(c, cudaEventRecord(c->snap_done[s], c->copy_stream));
+    c->snap_busy[s] = true;
+    return UVT_OK;
+}
+
+int uvt_readback_wait(uvt_ctx *c) {
+    if (!c) return UVT_ERR_INVALID;
+    for (int s = 0; s < 2; ++s)
+        if (c->snap_busy[s]) {
+            UVT_CUDA(c, cudaEventSynchronize(c->snap_done[s]));
+            c->snap_busy[s] = false;
+        }
     return UVT_OK;
 }
 

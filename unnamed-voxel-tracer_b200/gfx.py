@@ -204,6 +204,14 @@ class Context:
         kind, _, _ = self._KINDS[name]
         self.check(self.L.uvt_readback(self.handle, kind, pinned.ctypes.data, pinned.nbytes))
 
+    def readback_async(self, name, pinned):
+        """Pipelined readback into pinned host memory (see uvt_readback_async); pair with readback_wait()."""
+        kind, _, _ = self._KINDS[name]
+        self.check(self.L.uvt_readback_async(self.handle, kind, pinned.ctypes.data, pinned.nbytes))
+
+    def readback_wait(self):
+        self.check(self.L.uvt_readback_wait(self.handle))
+
     def count_pass(self, which):
         c = N.Counters()
         self.check(self.L.uvt_count_pass(self.handle, 0 if which == "primary" else 1, ctypes.byref(c)))
