@@ -30,9 +30,10 @@ with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
     f.write("| kernel | launches | mean us | total us | share |\n|---|---|---|---|---|\n")
     for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"| `{k}` | {len(v)} | {sum(v)/len(v):.1f} | {sum(v):.1f} | {100*sum(v)/total:.1f}% |\n")
-    f.write("\nNotes: `primary_kernel<WorldCompact, 0, 0>` is the timed step; `<..., 1, ...>` / `<..., 2, ...>` are the one-off counting variants run "
-            "outside the timed region; `FillFunctor` is the untimed 256 MiB L2 flush between timed steps; the `field_*`, `build_chunks2`, "
-            "`repack_bricks`, `brick_rowmask`, `clearance` kernels build the B200 layout once at `uvt_world_commit`.\n")
+    f.write("\nNotes: `primary_kernel<World, 0, ...>` is the timed step; `<World, 1, ...>` / `<World, 2, ...>` are the one-off counting variants run "
+            "outside the timed region; `FillFunctor` is the untimed 256 MiB L2 flush between timed steps; `l2_read_kernel` is the in-run L2 peak probe; "
+            "the `field_*`, `count_virtual`, `build_chunks2`, `repack_bricks`, `brick_rowmask`, `column_tops`, `quad_clear`, `clearance`, `dense_fill` "
+            "kernels build the B200 layout once at `uvt_world_commit`.\n")
 
 # ---- full capture of the dominant kernel
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
