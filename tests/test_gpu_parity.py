@@ -139,6 +139,20 @@ def test_every_kernel_variant_matches_the_oracle(uvt, oracle, scene_factory, var
             assert channel_diff(g["frame"], r["frame"]).max() <= 1
             assert ctx.count_pass("primary") == r["primary_counters"]
             assert ctx.count_pass("secondary") == r["secondary_counters"]
+        if not variant.startswith("fused"):  # a few random poses against the verbatim-trips kernel, GPU vs GPU
+            rng = np.random.default_rng(7)
+            ctx.resize(192, 108)
+            for i in range(10):
+                x, z = rng.uniform(20, 490, 2)
+                cam = oracle.make_camera((x, uvt.procgen.height(512, int(x), int(z)) + rng.uniform(2, 80), z),
+                                         pitch_yaw_matrix(uvt, rng.uniform(-1.2, 1.2), rng.uniform(0, 6.28)), fov=rng.uniform(0.5, 2.2))
+                ctx.set_layout("compact")
+                a = gpu_render(ctx, cam)
+                ctx.set_layout("reference")
+                b = gpu_render(ctx, cam)
+                ctx.set_layout("compact")
+                assert np.array_equal(a["hits"].view(np.uint8), b["hits"].view(np.uint8)), (variant, i)
+                assert np.array_equal(a["illumination"], b["illumination"]) and np.array_equal(a["frame"], b["frame"])
 
 
 @pytest.mark.parametrize("size", [(1, 1), (17, 9), (33, 31), (250, 130)])
@@ -469,3 +483,28 @@ def test_pipelined_readback_matches_blocking(uvt, oracle, w1):
     ctx.readback_wait()
     for buf, e in zip(bufs, expect):
         assert np.array_equal(buf.reshape(180, 320), e)
+
+
+def test_fast_path_vs_verbatim_kernel_many_poses(uvt, oracle, w1):
+    """Free trips, sealed rays and the dense grid against the verbatim-trips kernel on the reference layout (itself held
+    to the oracle above), GPU vs GPU, over many random poses: looking up, down, along the horizon, near map faces,
+    narrow and wide fields of view, primary and shadow pass."""
+    ctx, sc = w1
+    ctx.resize(256, 144)
+    rng = np.random.default_rng(2026)
+    for i in range(60):
+        near_face = i % 6 == 0
+        x, z = (rng.uniform(2, 30, 2) if near_face else rng.uniform(20, 490, 2))
+        if near_face and i % 12 == 0:
+            x, z = 512 - x, 512 - z
+        y = uvt.procgen.height(512, int(x), int(z)) + rng.uniform(1.5, 60 if i % 5 else 300)
+        pitch = rng.uniform(-1.5, 1.5) if i % 4 == 0 else rng.uniform(-0.5, 0.5)
+        cam = oracle.make_camera((x, y, z), pitch_yaw_matrix(uvt, pitch, rng.uniform(0, 2 * np.pi)), fov=rng.uniform(0.4, 2.3))
+        ctx.set_layout("compact")
+        a = gpu_render(ctx, cam)
+        ctx.set_layout("reference")
+        b = gpu_render(ctx, cam)
+        assert np.array_equal(a["hits"].view(np.uint8), b["hits"].view(np.uint8)), f"pose {i}"
+        for k in ("albedo", "normal", "illumination", "frame"):
+            assert np.array_equal(a[k], b[k]), (i, k)
+    ctx.set_layout("compact")

@@ -150,8 +150,11 @@ __device__ __forceinline__ void trace_map(const World &w, float ox, float oy, fl
     for (; trip < max_steps; ++trip) {
         // :107 — one unsigned compare per axis covers both < 0 and >= bound
         if ((unsigned)gx >= (unsigned)bound || (unsigned)gy >= (unsigned)bound || (unsigned)gz >= (unsigned)bound) {
+            // (the trip count is stored here and the function left at once: reading `trip` after a `break` out of this
+            // loop was observed to yield a wrong count with nvcc 12.9 -O3 on one ray of a 60-pose sweep)
             out.exit_kind = 2;
-            break;
+            out.trips = (uint32_t)trip;
+            return;
         }
         if (COUNT) tc.t_in++;
         const uint32_t px = (uint32_t)gx + __float2uint_rz(wx);  // :108
@@ -212,7 +215,7 @@ __device__ __forceinline__ void trace_map(const World &w, float ox, float oy, fl
         else if (mi == 1) { gy += posy ? istep : -istep; wy = posy ? 0.0f : reset; }
         else { gz += posz ? istep : -istep; wz = posz ? 0.0f : reset; }
     }
-    out.trips = (uint32_t)trip;
+    out.trips = (uint32_t)max(max_steps, 0);  // iteration cap reached (:167)
 }
 
 // ---- conservative "nothing ahead" test for climbing rays -------------------------------------
