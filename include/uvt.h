@@ -147,6 +147,20 @@ int  uvt_world_alloc(uvt_ctx *ctx, uint32_t dim, uint32_t **chunks_host, uint32_
 int  uvt_world_grow(uvt_ctx *ctx, size_t new_capacity, uint32_t **bricks_host);
 /* Make host edits visible to the GPU (H2D + repack kernel). n_bricks = GpuBlockAllocator.block_index. */
 int  uvt_world_commit(uvt_ctx *ctx, size_t n_bricks);
+/* Incremental publish: same result as uvt_world_commit(n_bricks) when the staging differs from
+ * the last committed state only inside the block box [lo, hi] (inclusive block coordinates, hi < dim) — the
+ * live-mapping semantics of VoxelBrickmap.set (voxel.zig:58-64) at interactive cost.  Existing chunk entries
+ * must be unchanged; new bricks (indices >= the previous n_bricks) may be attached to empty chunks of the box.
+ * Falls back to a full commit by itself whenever the in-place path does not apply (first commit, box of more
+ * than 4096 chunks, no spare brick slots, more than 223 materials). */
+int  uvt_world_commit_region(uvt_ctx *ctx, size_t n_bricks, const uint32_t lo[3], const uint32_t hi[3]);
+/* map_setVoxel (map.glsl:49-55): writes the block word into the staging AND publishes it, but only where the
+ * chunk already holds a brick (the shader never allocates); *written (may be NULL) tells which. */
+int  uvt_world_set_voxel(uvt_ctx *ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t voxel, int *written);
+/* Checksums of the layout the commit derived (test hook: an incremental commit must leave exactly what a full
+ * commit builds).  Keyed by block position, independent of brick numbering: out[0] dense grid, out[1] brick
+ * view (brick bytes + far-empty chunk entries), out[2] column-group tops, out[3] = y_clear | n_materials << 32. */
+int  uvt_world_layout_checksum(uvt_ctx *ctx, uint64_t out[4]);
 
 /* ---- atlas: VoxelModelAtlas → Texture.set_data_offset → glTextureSubImage3D
  *      (voxel.zig:88-131, texture.zig:70-72): RGBA8 sub-box, x fastest then y then z. */

@@ -45,8 +45,12 @@ size_t   uvt_brickmap_n_bricks(const uvt_brickmap *bm);      /* GpuBlockAllocato
 size_t   uvt_brickmap_capacity(const uvt_brickmap *bm);      /* GpuBlockAllocator.max_block_index */
 const uint32_t *uvt_brickmap_chunks(const uvt_brickmap *bm); /* u32[(dim/8)^3]      */
 const uint32_t *uvt_brickmap_bricks(const uvt_brickmap *bm); /* u32[capacity][512]  */
-/* VoxelBrickmap.bind (voxel.zig:77-80): publish to the attached ctx (uvt_world_commit). */
+/* VoxelBrickmap.bind (voxel.zig:77-80; called every frame, game.zig:236): publish to the attached ctx.
+ * The first bind is a full uvt_world_commit; later binds publish only the box of blocks written through
+ * uvt_brickmap_set since the previous bind (uvt_world_commit_region) and cost nothing when the map is clean.
+ * Writes made through the raw pointers above are not tracked: call uvt_brickmap_mark_dirty after them. */
 int      uvt_brickmap_bind(uvt_brickmap *bm);
+void     uvt_brickmap_mark_dirty(uvt_brickmap *bm);
 /* Reproducible world dump: "UVTW" u32 version, dim, n_bricks, chunks[], bricks[n][512]. */
 int      uvt_brickmap_save(const uvt_brickmap *bm, const char *path);
 int      uvt_brickmap_load(uvt_ctx *ctx, const char *path, uvt_brickmap **out);

@@ -508,3 +508,140 @@ def test_fast_path_vs_verbatim_kernel_many_poses(uvt, oracle, w1):
         for k in ("albedo", "normal", "illumination", "frame"):
             assert np.array_equal(a[k], b[k]), (i, k)
     ctx.set_layout("compact")
+
+
+# ---- incremental publish: uvt_world_commit_region / uvt_world_set_voxel / bind() of a dirty box ------
+def _fresh_full_commit(uvt, sc, tmp_path, **ctx_kw):
+    """A second ctx holding the same host world, published by one full commit."""
+    path = str(tmp_path / "world.uvtw")
+    sc.bm.save(path)
+    ctx = uvt.Context(0, hit_buffer=True, **ctx_kw)
+    bm = uvt.voxel.VoxelBrickmap.load(path, ctx)
+    atlas = uvt.voxel.VoxelModelAtlas.init(ctx)
+    for m in sc.models:
+        atlas.append_model(m)
+    bm.bind(9)
+    return ctx, bm
+
+
+def _same_render(a, b):
+    assert np.array_equal(a["hits"].view(np.uint8), b["hits"].view(np.uint8))
+    for k in ("albedo", "normal", "position", "illumination", "frame"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("dense", [True, False])
+def test_incremental_commit_equals_full_commit(uvt, oracle, scene_factory, tmp_path, dense):
+    """Edits published through bind() (dirty box -> uvt_world_commit_region) leave the same derived layout
+    (checksums) and the same pixels as a fresh full commit of the edited world; hits match the oracle."""
+    V = uvt.voxel.Voxel
+    rng = np.random.default_rng(11)
+    dim = 128
+    with uvt.Context(0, hit_buffer=True, dense=dense) as ctx:
+        sc = scene_factory(dim, "procgen", ctx=ctx)
+        ctx.resize(160, 96)
+        cams = [oracle.make_camera((64.0, 30.0, 40.0)),
+                oracle.make_camera((30.0, 45.0, 30.0), pitch_yaw_matrix(uvt, 0.5, 0.8)),
+                oracle.make_camera((100.0, 60.0, 100.0), pitch_yaw_matrix(uvt, 0.9, 3.9))]
+
+        def edits(step):
+            if step == 0:    # dig: remove blocks inside existing bricks
+                for _ in range(40):
+                    x, z = (int(v) for v in rng.integers(40, 90, 2))
+                    for y in range(10, 24):
+                        if sc.bm.get(x, y, z):
+                            sc.bm.set(x, y, z, 0)
+            elif step == 1:  # build inside existing bricks and just above them
+                for _ in range(30):
+                    x, z = (int(v) for v in rng.integers(50, 80, 2))
+                    sc.bm.set(x, int(rng.integers(16, 24)), z, V(11, True))
+            elif step == 2:  # a floating slab in empty air: new bricks, new virtual bricks, new chunk distances
+                for x in range(60, 71):
+                    for z in range(44, 52):
+                        sc.bm.set(x, 52, z, V(13, True))
+            elif step == 3:  # single block at the map corner and one at the top face
+                sc.bm.set(0, 40, 0, V(11, True))
+                sc.bm.set(dim - 1, dim - 1, dim - 1, V(11, True))
+            elif step == 4:  # remove part of the slab again (bricks stay allocated, chunks stay non-empty)
+                for x in range(60, 66):
+                    for z in range(44, 52):
+                        sc.bm.set(x, 52, z, 0)
+            elif step == 5:  # a tall pillar crossing many chunk rows
+                for y in range(0, 100):
+                    sc.bm.set(20, y, 90, V(21, True))
+
+        for step in range(6):
+            edits(step)
+            launches0 = ctx.launch_count()
+            sc.bm.bind(9)
+            n_launch = ctx.launch_count() - launches0
+            assert 0 < n_launch < 20, n_launch
+            ctx2, bm2 = _fresh_full_commit(uvt, sc, tmp_path, dense=dense)
+            try:
+                assert ctx.world_layout_checksum()[:4] == ctx2.world_layout_checksum()[:4], step
+                ctx2.resize(160, 96)
+                world = oracle.World(dim, sc.bm.chunks().copy(), sc.bm.bricks().copy(), sc.oracle_world.atlas)
+                for cam in cams:
+                    a, b = gpu_render(ctx, cam), gpu_render(ctx2, cam)
+                    _same_render(a, b)
+                    assert ctx.count_pass("primary") == ctx2.count_pass("primary")
+                    assert_primary_parity(a, oracle.render(world, cam, 160, 96))
+            finally:
+                ctx2.close()
+        # a clean map: bind() is free
+        launches0 = ctx.launch_count()
+        sc.bm.bind(9)
+        assert ctx.launch_count() == launches0
+
+
+def test_incremental_commit_new_material_and_set_voxel(uvt, oracle, scene_factory, tmp_path):
+    """A block word never seen before gets a material id in place; uvt_world_set_voxel follows map_setVoxel."""
+    V = uvt.voxel.Voxel
+    dim = 128
+    with uvt.Context(0, hit_buffer=True) as ctx:
+        sc = scene_factory(dim, "procgen", ctx=ctx)
+        ctx.resize(160, 96)
+        cam = oracle.make_camera((64.0, 30.0, 40.0))
+        before = gpu_render(ctx, cam)
+        n_mats = ctx.world_layout_checksum()[4]
+        for x in range(60, 68):
+            for y in range(18, 30):
+                sc.bm.set(x, y, 60, V(5, False))    # model 5 without the "solid" flag: a new block word
+        sc.bm.bind(9)
+        assert ctx.world_layout_checksum()[4] == n_mats + 1
+        world = oracle.World(dim, sc.bm.chunks().copy(), sc.bm.bricks().copy(), sc.oracle_world.atlas)
+        after = gpu_render(ctx, cam)
+        assert_primary_parity(after, oracle.render(world, cam, 160, 96))
+        assert not np.array_equal(before["hits"]["block"], after["hits"]["block"])
+        ctx2, _ = _fresh_full_commit(uvt, sc, tmp_path)
+        try:
+            ctx2.resize(160, 96)
+            _same_render(after, gpu_render(ctx2, cam))
+        finally:
+            ctx2.close()
+        # map_setVoxel: lands in an existing brick, ignored in an empty chunk and outside the map
+        assert ctx.world_set_voxel(64, 15, 45, V(11, True)) is True
+        assert ctx.world_set_voxel(64, 120, 45, V(11, True)) is False
+        assert ctx.world_set_voxel(dim, 20, 45, V(11, True)) is False
+        assert sc.bm.get(64, 15, 45) == V(11, True) and sc.bm.get(64, 120, 45) == 0
+        world = oracle.World(dim, sc.bm.chunks().copy(), sc.bm.bricks().copy(), sc.oracle_world.atlas)
+        assert_primary_parity(gpu_render(ctx, cam), oracle.render(world, cam, 160, 96))
+
+
+def test_incremental_commit_on_w1_near_camera(uvt, oracle, scene_factory):
+    """W1 at K0: a wall built block by block, one bind per block (the interactive editing pattern)."""
+    V = uvt.voxel.Voxel
+    with uvt.Context(0, hit_buffer=True) as ctx:
+        sc = scene_factory(512, "procgen", ctx=ctx)
+        ctx.resize(160, 90)
+        cam = camera_k0(oracle)
+        for i, (x, y) in enumerate((x, y) for y in range(22, 34) for x in range(252, 260)):
+            sc.bm.set(x, y, 266, V(11, True))
+            sc.bm.bind(9)
+            if i % 24 == 23:
+                world = oracle.World(512, sc.bm.chunks().copy(), sc.bm.bricks().copy(), sc.oracle_world.atlas)
+                assert_primary_parity(gpu_render(ctx, cam), oracle.render(world, cam, 160, 90))
+        ctx.set_layout("reference")
+        ref = gpu_render(ctx, cam)
+        ctx.set_layout("compact")
+        _same_render(gpu_render(ctx, cam), ref)

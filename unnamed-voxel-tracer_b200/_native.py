@@ -67,6 +67,9 @@ SIGNATURES = {
     "uvt_world_alloc": (c_int, [c_p, c_u32, P(c_p), P(c_p), c_size]),
     "uvt_world_grow": (c_int, [c_p, c_size, P(c_p)]),
     "uvt_world_commit": (c_int, [c_p, c_size]),
+    "uvt_world_commit_region": (c_int, [c_p, c_size, P(c_u32 * 3), P(c_u32 * 3)]),
+    "uvt_world_set_voxel": (c_int, [c_p, c_u32, c_u32, c_u32, c_u32, P(c_int)]),
+    "uvt_world_layout_checksum": (c_int, [c_p, P(ctypes.c_uint64 * 4)]),
     "uvt_atlas_upload": (c_int, [c_p, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, c_p]),
     "uvt_set_camera": (c_int, [c_p, c_p]),
     "uvt_set_cameras": (c_int, [c_p, c_p, c_int]),
@@ -111,6 +114,7 @@ SIGNATURES = {
     "uvt_brickmap_chunks": (c_p, [c_p]),
     "uvt_brickmap_bricks": (c_p, [c_p]),
     "uvt_brickmap_bind": (c_int, [c_p]),
+    "uvt_brickmap_mark_dirty": (None, [c_p]),
     "uvt_brickmap_save": (c_int, [c_p, ctypes.c_char_p]),
     "uvt_brickmap_load": (c_int, [c_p, ctypes.c_char_p, P(c_p)]),
     "uvt_procgen": (c_int, [c_p, c_u32, c_f, c_f]),

@@ -20,6 +20,9 @@ struct uvt_brickmap {
     uint32_t *bricks = nullptr;
     size_t block_index = 0;      // next free brick
     size_t max_block_index = 0;  // capacity in bricks
+    // blocks written since the last bind (uvt_brickmap_bind publishes only what changed)
+    bool bound = false, dirty = true, dirty_all = true;
+    uint32_t dirty_lo[3] = {0, 0, 0}, dirty_hi[3] = {0, 0, 0};
 };
 
 namespace {
@@ -105,6 +108,11 @@ void uvt_brickmap_clear(uvt_brickmap *bm) {
     std::memset(bm->chunks, 0, n_chunks * sizeof(uint32_t));
     bm->block_index = 0;
     std::memset(bm->bricks, 0, bm->max_block_index * kBrickWords * sizeof(uint32_t));
+    bm->dirty = bm->dirty_all = true;
+}
+
+void uvt_brickmap_mark_dirty(uvt_brickmap *bm) {
+    if (bm) bm->dirty = bm->dirty_all = true;
 }
 
 int uvt_brickmap_set(uvt_brickmap *bm, uint32_t x, uint32_t y, uint32_t z, uint32_t voxel) {
@@ -113,6 +121,12 @@ int uvt_brickmap_set(uvt_brickmap *bm, uint32_t x, uint32_t y, uint32_t z, uint3
     int rc = block_for_chunk(bm, x / kChunk, y / kChunk, z / kChunk, &blk);
     if (rc != UVT_OK) return rc;
     bm->bricks[blk * kBrickWords + (x % kChunk) + ((y % kChunk) + (z % kChunk) * kChunk) * kChunk] = voxel;
+    const uint32_t p[3] = {x, y, z};
+    for (int a = 0; a < 3; ++a) {
+        bm->dirty_lo[a] = bm->dirty ? std::min(bm->dirty_lo[a], p[a]) : p[a];
+        bm->dirty_hi[a] = bm->dirty ? std::max(bm->dirty_hi[a], p[a]) : p[a];
+    }
+    bm->dirty = true;
     return UVT_OK;
 }
 
@@ -136,7 +150,14 @@ const uint32_t *uvt_brickmap_bricks(const uvt_brickmap *bm) { return bm->bricks;
 
 int uvt_brickmap_bind(uvt_brickmap *bm) {
     if (!bm->ctx) return UVT_ERR_INVALID;
-    return uvt_world_commit(bm->ctx, bm->block_index);
+    // the reference's mapping is live and bind() is a per-frame GL call (game.zig:236): publish only what was written
+    int rc = UVT_OK;
+    if (!bm->bound || bm->dirty_all) rc = uvt_world_commit(bm->ctx, bm->block_index);
+    else if (bm->dirty) rc = uvt_world_commit_region(bm->ctx, bm->block_index, bm->dirty_lo, bm->dirty_hi);
+    if (rc != UVT_OK) return rc;
+    bm->bound = true;
+    bm->dirty = bm->dirty_all = false;
+    return UVT_OK;
 }
 
 int uvt_brickmap_save(const uvt_brickmap *bm, const char *path) {

@@ -492,6 +492,7 @@ __global__ void repack_bricks_kernel(const uint32_t *__restrict__ bricks, uint8_
 // dist[c] = Chebyshev distance (in chunks) from chunk c to the nearest NON-EMPTY chunk or to the
 // outside of the map, capped at kFieldCap; separable min-max passes over x, y, z.
 constexpr int kFieldCap = 32;
+constexpr uint32_t kNoChunk = 0xFFFFFFFFu;  // brick_chunk[] of a brick slot no chunk uses
 
 __global__ void field_pass_x_kernel(const uint32_t *__restrict__ chunks, uint8_t *__restrict__ out, int cd) {
     const size_t n = (size_t)cd * cd * cd;
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(64) column_tops_kernel(const uint8_t *__restri
                                                          unsigned int *__restrict__ tops32) {
     const uint32_t b = blockIdx.x;
     const uint32_t cj = brick_chunk[b];
+    if (cj == kNoChunk) return;  // a brick no chunk names
     const int cx = (int)(cj % cd), cy = (int)((cj / cd) % cd), cz = (int)(cj / ((uint32_t)cd * cd));
     const int lx = threadIdx.x & 7, lz = threadIdx.x >> 3;
     const int dim = cd * 8;
@@ -611,12 +613,9 @@ __global__ void quad_clear_kernel(const unsigned int *__restrict__ tops32, uint1
 // empty block searches growing Chebyshev shells for the nearest occupied block, D capped at 16, and
 // stores kMatLimit + max(D - 2, 0) (see trace_map_fast for the bound).
 constexpr int kClearCap = 16;
-__global__ void __launch_bounds__(512) clearance_kernel(const uint32_t *__restrict__ chunks2, int cd, const uint32_t *__restrict__ brick_chunk,
-                                                        const uint8_t *__restrict__ rowmask, uint8_t *__restrict__ bricks8) {
-    __shared__ unsigned long long rows[40 * 40];  // [z'][y'], bit i = x' = i - 16 relative to the brick origin
-    const uint32_t b = blockIdx.x;
-    const uint32_t cj = brick_chunk[b];
-    const int cx = (int)(cj % cd), cy = (int)((cj / cd) % cd), cz = (int)(cj / ((uint32_t)cd * cd));
+
+__device__ __forceinline__ void clearance_brick(const uint32_t *__restrict__ chunks2, int cd, uint32_t b, int cx, int cy, int cz,
+                                                const uint8_t *__restrict__ rowmask, uint8_t *__restrict__ bricks8, unsigned long long *rows) {
     const int cd1 = cd + 1;
     for (int r = threadIdx.x; r < 40 * 40; r += blockDim.x) {
         const int yy = r % 40, zz = r / 40;                 // 0..39 -> block offset -16..23
@@ -638,7 +637,8 @@ __global__ void __launch_bounds__(512) clearance_kernel(const uint32_t *__restri
     __syncthreads();
     const int lx = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7, lz = threadIdx.x >> 6;
     const size_t addr = (size_t)b * 512u + threadIdx.x;
-    if (bricks8[addr] != 0) return;  // material block
+    const uint8_t cur = bricks8[addr];
+    if (cur != 0 && cur < kMatLimit) return;  // material block (a stale clearance code is recomputed)
     const int x0 = lx + 16, y0 = ly + 16, z0 = lz + 16;
     int D = kClearCap;
     for (int r = 1; r < kClearCap; ++r) {
@@ -658,13 +658,32 @@ __global__ void __launch_bounds__(512) clearance_kernel(const uint32_t *__restri
     bricks8[addr] = (uint8_t)(kMatLimit + max(D - 2, 0));
 }
 
+// all bricks (full commit): one CTA per brick slot
+__global__ void __launch_bounds__(512) clearance_kernel(const uint32_t *__restrict__ chunks2, int cd, const uint32_t *__restrict__ brick_chunk,
+                                                        const uint8_t *__restrict__ rowmask, uint8_t *__restrict__ bricks8) {
+    __shared__ unsigned long long rows[40 * 40];  // [z'][y'], bit i = x' = i - 16 relative to the brick origin
+    const uint32_t b = blockIdx.x;
+    const uint32_t cj = brick_chunk[b];
+    if (cj == kNoChunk) return;
+    clearance_brick(chunks2, cd, b, (int)(cj % cd), (int)((cj / cd) % cd), (int)(cj / ((uint32_t)cd * cd)), rowmask, bricks8, rows);
+}
+
+// the bricks of a chunk box (incremental commit): grid = box extent, origin (ox, oy, oz)
+__global__ void __launch_bounds__(512) clearance_box_kernel(const uint32_t *__restrict__ chunks2, int cd, int ox, int oy, int oz,
+                                                            const uint8_t *__restrict__ rowmask, uint8_t *__restrict__ bricks8) {
+    __shared__ unsigned long long rows[40 * 40];
+    const int cx = ox + (int)blockIdx.x, cy = oy + (int)blockIdx.y, cz = oz + (int)blockIdx.z;
+    const int cd1 = cd + 1;
+    const uint32_t e = chunks2[(size_t)cx + (size_t)cd1 * ((size_t)cy + (size_t)cz * cd1)];
+    if ((int)e < 0) return;  // far-empty chunk: no brick
+    clearance_brick(chunks2, cd, e, cx, cy, cz, rowmask, bricks8, rows);
+}
+
 // Dense block grid for the traversal kernels: dense[x + dim*(z + dim*y)] = the brick byte of block (x, y, z);
 // blocks of far-empty chunks get kMatLimit + min(n_free, 30) of their chunk.  One CTA per chunk, one thread per x-row.
-__global__ void __launch_bounds__(64) dense_fill_kernel(const uint32_t *__restrict__ chunks2, const uint8_t *__restrict__ bricks8,
-                                                        uint8_t *__restrict__ dense, int cd) {
+__device__ __forceinline__ void dense_fill_chunk(const uint32_t *__restrict__ chunks2, const uint8_t *__restrict__ bricks8,
+                                                 uint8_t *__restrict__ dense, int cd, int cx, int cy, int cz) {
     const int cd1 = cd + 1;
-    const size_t cj = blockIdx.x;
-    const int cx = (int)(cj % cd), cy = (int)((cj / cd) % cd), cz = (int)(cj / ((size_t)cd * cd));
     const int ly = threadIdx.x & 7, lz = threadIdx.x >> 3;
     const uint32_t e = chunks2[(size_t)cx + (size_t)cd1 * ((size_t)cy + (size_t)cz * cd1)];
     uint2 v;
@@ -676,6 +695,187 @@ __global__ void __launch_bounds__(64) dense_fill_kernel(const uint32_t *__restri
     }
     const size_t dim = (size_t)cd * 8;
     *reinterpret_cast<uint2 *>(dense + (size_t)cx * 8 + dim * ((size_t)(cz * 8 + lz) + dim * (size_t)(cy * 8 + ly))) = v;
+}
+
+__global__ void __launch_bounds__(64) dense_fill_kernel(const uint32_t *__restrict__ chunks2, const uint8_t *__restrict__ bricks8,
+                                                        uint8_t *__restrict__ dense, int cd) {
+    const size_t cj = blockIdx.x;
+    dense_fill_chunk(chunks2, bricks8, dense, cd, (int)(cj % cd), (int)((cj / cd) % cd), (int)(cj / ((size_t)cd * cd)));
+}
+
+__global__ void __launch_bounds__(64) dense_fill_box_kernel(const uint32_t *__restrict__ chunks2, const uint8_t *__restrict__ bricks8,
+                                                            uint8_t *__restrict__ dense, int cd, int ox, int oy, int oz) {
+    dense_fill_chunk(chunks2, bricks8, dense, cd, ox + (int)blockIdx.x, oy + (int)blockIdx.y, oz + (int)blockIdx.z);
+}
+
+__global__ void __launch_bounds__(64) dense_fill_list_kernel(const uint32_t *__restrict__ chunks2, const uint8_t *__restrict__ bricks8,
+                                                             uint8_t *__restrict__ dense, int cd, const uint32_t *__restrict__ list) {
+    const uint32_t cj = list[blockIdx.x];
+    dense_fill_chunk(chunks2, bricks8, dense, cd, (int)(cj % cd), (int)((cj / cd) % cd), (int)(cj / ((uint32_t)cd * cd)));
+}
+
+// ---- incremental commit (uvt_world_commit_region) ---------------------------------
+// Write the chunk entries of a box into the device table; *changed is set when any entry differs from the committed one.
+__global__ void apply_chunk_box_kernel(uint32_t *__restrict__ chunks, const uint32_t *__restrict__ ents, int cd, int ox, int oy, int oz,
+                                       int bx, int by, int bz, unsigned int *changed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bx * by * bz) return;
+    const int x = ox + i % bx, y = oy + (i / bx) % by, z = oz + i / (bx * by);
+    const size_t j = (size_t)x + (size_t)cd * ((size_t)y + (size_t)z * cd);
+    const uint32_t e = ents[i];
+    if (chunks[j] != e) {
+        chunks[j] = e;
+        atomicOr(changed, 1u);
+    }
+}
+
+// Repack listed bricks (u32 words -> material bytes) and refresh their row masks.  One CTA per brick, one thread per x-row.
+__global__ void __launch_bounds__(64) repack_list_kernel(const uint32_t *__restrict__ bricks, uint8_t *__restrict__ bricks8, uint8_t *__restrict__ rowmask,
+                                                         const uint32_t *__restrict__ list, const uint32_t *__restrict__ lut_keys,
+                                                         const uint8_t *__restrict__ lut_vals, uint32_t lut_mask) {
+    const size_t b = list[blockIdx.x];
+    const size_t row = b * 64u + threadIdx.x;
+    const uint4 lo = *reinterpret_cast<const uint4 *>(bricks + row * 8u), hi = *reinterpret_cast<const uint4 *>(bricks + row * 8u + 4u);
+    const uint32_t wds[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t packed[2] = {0u, 0u}, mask = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t m = 0;
+        if (wds[k] != 0) {
+            uint32_t hsh = (wds[k] * 2654435761u) & lut_mask;
+            while (lut_keys[hsh] != wds[k]) hsh = (hsh + 1u) & lut_mask;
+            m = lut_vals[hsh];
+            mask |= 1u << k;
+        }
+        packed[k >> 2] |= m << (8 * (k & 3));
+    }
+    *reinterpret_cast<uint2 *>(bricks8 + row * 8u) = make_uint2(packed[0], packed[1]);
+    rowmask[row] = (uint8_t)mask;
+}
+
+// empty chunks that newly touch a non-empty chunk and hold no virtual brick yet
+__global__ void count_new_virtual_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ dist, const uint32_t *__restrict__ chunks2,
+                                         int cd, uint32_t v_base, unsigned int *counter) {
+    const size_t n = (size_t)cd * cd * cd;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool v = false;
+    if (j < n && chunks[j] == 0 && dist[j] == 1) {
+        const int cd1 = cd + 1;
+        const int x = (int)(j % cd), y = (int)((j / cd) % cd), z = (int)(j / ((size_t)cd * cd));
+        const uint32_t old = chunks2[(size_t)x + (size_t)cd1 * ((size_t)y + (size_t)z * cd1)];
+        v = (int)old < 0 || old < v_base;
+    }
+    const unsigned int m = __ballot_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31u) == 0 && m) atomicAdd(counter, (unsigned int)__popc(m));
+}
+
+// chunks2 after a chunk-table change: real and existing virtual bricks keep their slots, new virtual bricks are
+// appended (zeroed), far-empty distances are refreshed; every chunk whose entry changed is listed (dense refill).
+__global__ void update_chunks2_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ dist, uint32_t *__restrict__ chunks2,
+                                      uint32_t *__restrict__ brick_chunk, uint8_t *__restrict__ bricks8, uint8_t *__restrict__ rowmask, int cd,
+                                      uint32_t v_base, unsigned int *n_virtual, uint32_t *__restrict__ changed_list, uint32_t changed_cap,
+                                      unsigned int *changed_count) {
+    const size_t n = (size_t)cd * cd * cd;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int cd1 = cd + 1;
+    const int x = (int)(j % cd), y = (int)((j / cd) % cd), z = (int)(j / ((size_t)cd * cd));
+    const size_t i = (size_t)x + (size_t)cd1 * ((size_t)y + (size_t)z * cd1);
+    const uint32_t old = chunks2[i];
+    const uint32_t c = chunks[j];
+    uint32_t e;
+    if (c != 0) {
+        e = c - 1u;
+        brick_chunk[e] = (uint32_t)j;
+    } else if (dist[j] == 1) {
+        if ((int)old >= 0 && old >= v_base) e = old;
+        else {
+            e = v_base + atomicAdd(n_virtual, 1u);  // capacity was checked with count_new_virtual_kernel
+            brick_chunk[e] = (uint32_t)j;
+            uint4 *b8 = reinterpret_cast<uint4 *>(bricks8 + (size_t)e * 512u);
+            for (int k = 0; k < 32; ++k) b8[k] = make_uint4(0u, 0u, 0u, 0u);
+            uint4 *rm = reinterpret_cast<uint4 *>(rowmask + (size_t)e * 64u);
+            for (int k = 0; k < 4; ++k) rm[k] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    } else {
+        const int r = (int)dist[j] - 1;
+        e = 0x80000000u | (uint32_t)min(max(8 * r - 1, 0), 255);
+    }
+    if (e != old) {
+        chunks2[i] = e;
+        const unsigned int k = atomicAdd(changed_count, 1u);
+        if (k < changed_cap) changed_list[k] = (uint32_t)j;
+    }
+}
+
+// column tops of the real bricks in the chunk columns [ox, ox+gridDim.x) x [oz, oz+gridDim.z), all chunk rows (gridDim.y = cd)
+__global__ void __launch_bounds__(64) column_tops_box_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ bricks8, int cd,
+                                                             int ox, int oz, unsigned int *__restrict__ tops32) {
+    const int cx = ox + (int)blockIdx.x, cy = (int)blockIdx.y, cz = oz + (int)blockIdx.z;
+    const uint32_t c = chunks[(size_t)cx + (size_t)cd * ((size_t)cy + (size_t)cz * cd)];
+    if (c == 0) return;
+    const size_t b = c - 1u;
+    const int lx = threadIdx.x & 7, lz = threadIdx.x >> 3;
+    const int dim = cd * 8;
+    for (int ly = 7; ly >= 0; --ly) {
+        const uint8_t v = bricks8[b * 512u + lx + 8 * ly + 64 * lz];
+        if (v != 0 && v < kMatLimit) {
+            atomicMax(&tops32[(size_t)(cx * 8 + lx) + (size_t)dim * (cz * 8 + lz)], (unsigned int)(cy * 8 + ly + 1));
+            break;
+        }
+    }
+}
+
+// y_clear = max over clear4 (= max over the column tops: clear4 is a dilated max of them)
+__global__ void max_clear_kernel(const uint16_t *__restrict__ clear4, int n, unsigned int *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int v = i < n ? clear4[i] : 0u;
+    v = __reduce_max_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31u) == 0 && v) atomicMax(out, v);
+}
+
+// ---- layout checksum (tests: an incremental commit must leave what a full commit builds) ----
+// Position-keyed sums, independent of brick slot numbering: out[0] over the dense grid bytes (materials by block word), out[1] over
+// the brick-path view (brick bytes by global block, far-empty entries by chunk), out[2] over clear4.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+__global__ void __launch_bounds__(64) layout_checksum_kernel(const uint32_t *__restrict__ chunks2, const uint8_t *__restrict__ bricks8,
+                                                             const uint8_t *__restrict__ dense, const uint32_t *__restrict__ mat_word, int cd,
+                                                             unsigned long long *out) {
+    // material bytes enter as their block word (ids depend on the order materials were first seen), clearances as they are
+    auto val = [&](uint32_t v) -> unsigned long long { return v < kMatLimit ? (unsigned long long)mat_word[v] + 1ull : 0x100000000ull + v; };
+    const size_t cj = blockIdx.x;
+    const int cx = (int)(cj % cd), cy = (int)((cj / cd) % cd), cz = (int)(cj / ((size_t)cd * cd));
+    const int cd1 = cd + 1;
+    const int ly = threadIdx.x & 7, lz = threadIdx.x >> 3;
+    const size_t dim = (size_t)cd * 8;
+    const uint32_t e = chunks2[(size_t)cx + (size_t)cd1 * ((size_t)cy + (size_t)cz * cd1)];
+    unsigned long long hd = 0, hb = 0;
+    for (int lx = 0; lx < 8; ++lx) {
+        const size_t g = (size_t)(cx * 8 + lx) + dim * ((size_t)(cz * 8 + lz) + dim * (size_t)(cy * 8 + ly));
+        const unsigned long long key = mix64(g + 1) | 1ull;
+        if (dense) hd += val(dense[g]) * key;
+        if ((int)e >= 0) hb += val(bricks8[(size_t)e * 512u + lx + 8 * ly + 64 * lz]) * key;
+    }
+    if ((int)e < 0 && threadIdx.x == 0) hb += (unsigned long long)(e & 0xFFu) * (mix64(cj + 0x9e3779b97f4a7c15ull) | 1ull) + 0x5bd1e995ull;
+    for (int o = 16; o > 0; o >>= 1) {
+        hd += __shfl_xor_sync(0xFFFFFFFFu, hd, o);
+        hb += __shfl_xor_sync(0xFFFFFFFFu, hb, o);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        if (hd) atomicAdd(out + 0, hd);
+        if (hb) atomicAdd(out + 1, hb);
+    }
+}
+
+__global__ void clear4_checksum_kernel(const uint16_t *__restrict__ clear4, int n, unsigned long long *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long h = i < n ? (unsigned long long)(clear4[i] + 1u) * (mix64((unsigned long long)i + 7ull) | 1ull) : 0ull;
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+    if ((threadIdx.x & 31u) == 0 && h) atomicAdd(out + 2, h);
 }
 
 // ---- bandwidth probes (roofline denominators) ----------------------------------

@@ -49,7 +49,14 @@ struct uvt_ctx {
     uint8_t *d_bricks8 = nullptr;
     size_t d_brick8_capacity = 0;
     uint32_t *d_chunks2 = nullptr;  // fast-path chunk table [(cd+1)^3]
-    size_t n_total_bricks = 0;      // real + virtual (clearance-only) bricks in d_bricks8
+    size_t n_total_bricks = 0;      // brick slots in use in d_bricks8: real [0, n_bricks), spare, virtual [v_base, v_base + n_virtual)
+    size_t v_base = 0;              // first virtual (clearance-only) brick slot; the spare slots below it take new real bricks
+    size_t n_virtual = 0;
+    uint8_t *d_rowmask = nullptr;       // [d_brick8_capacity][64] x-occupancy bits of every brick row
+    uint32_t *d_brick_chunk = nullptr;  // [d_brick8_capacity] brick slot -> linear chunk index (kNoChunk: unused)
+    unsigned int *d_tops32 = nullptr;   // [dim^2] column tops (block y + 1)
+    uint32_t *d_scratch = nullptr;      // staging of uvt_world_commit_region (kScratchWords)
+    bool incremental_ok = false;        // the last full commit left everything uvt_world_commit_region needs
     int32_t y_clear = 0;            // max occupied block y + 1 (every block at or above is empty)
     uint16_t *d_clear4 = nullptr;   // [(dim/4)^2] dilated column-group tops for sky_sealed()
     uint8_t *d_dense = nullptr;     // [dim^3] dense block grid (nullptr: not built — too large or disabled)
@@ -393,16 +400,55 @@ int launch_secondary(uvt_ctx *c) {
 
 // Build the B200 layout from the committed reference layout (all on the device):
 // chunk distance field -> virtual bricks -> chunks2, 8-bit material bricks, block clearances.
+// scratch layout of uvt_world_commit_region (32-bit words)
+constexpr size_t kScrEnts = 0, kMaxBoxChunks = 4096;                 // chunk entries of the box
+constexpr size_t kScrList = kScrEnts + kMaxBoxChunks, kMaxListBricks = 8192;  // bricks to repack
+constexpr size_t kScrKeys = kScrList + kMaxListBricks, kLutSize = 1024;
+constexpr size_t kScrVals = kScrKeys + kLutSize;                      // kLutSize bytes
+constexpr size_t kScrFlags = kScrVals + kLutSize / 4;                 // 8 counters / flags
+constexpr size_t kScrChanged = kScrFlags + 8, kMaxChanged = 65536;    // chunks whose chunks2 entry changed
+constexpr size_t kScratchWords = kScrChanged + kMaxChanged;
+
+// open-addressed block word -> material id table for the repack kernels
+int upload_material_lut(uvt_ctx *c, uint32_t *d_keys, uint8_t *d_vals) {
+    std::vector<uint32_t> keys(kLutSize, 0);
+    std::vector<uint8_t> vals(kLutSize, 0);
+    const uint32_t lut_mask = (uint32_t)kLutSize - 1;
+    for (size_t m = 1; m < c->mat_words.size(); ++m) {
+        uint32_t h = (c->mat_words[m] * 2654435761u) & lut_mask;
+        while (keys[h] != 0) h = (h + 1) & lut_mask;
+        keys[h] = c->mat_words[m];
+        vals[h] = (uint8_t)m;
+    }
+    UVT_CUDA(c, cudaMemcpyAsync(d_keys, keys.data(), kLutSize * 4, cudaMemcpyHostToDevice, c->stream));
+    UVT_CUDA(c, cudaMemcpyAsync(d_vals, vals.data(), kLutSize, cudaMemcpyHostToDevice, c->stream));
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));  // the staging vectors die at scope exit
+    return UVT_OK;
+}
+
+// clear4 from the column tops, then y_clear = its maximum
+int finish_tops(uvt_ctx *c, unsigned int *d_max) {
+    const int nq = (int)((c->dim / 4) * (c->dim / 4));
+    quad_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_tops32, c->d_clear4, (int)c->dim);
+    UVT_CUDA(c, cudaMemsetAsync(d_max, 0, 4, c->stream));
+    max_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, nq, d_max);
+    c->launches += 2;
+    unsigned int top = 0;
+    UVT_CUDA(c, cudaMemcpyAsync(&top, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->y_clear = (int32_t)top;
+    return UVT_OK;
+}
+
+// Build the B200 layout from the committed reference layout (all on the device):
+// chunk distance field -> virtual bricks -> chunks2, 8-bit material bricks, block clearances.
 int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
     const int cd = (int)c->cd;
     const size_t n_chunks = (size_t)cd * cd * cd;
     const size_t n2 = (size_t)(cd + 1) * (cd + 1) * (cd + 1);
-    uint8_t *f0 = nullptr, *f1 = nullptr, *rowmask = nullptr, *d_vals = nullptr;
-    uint32_t *d_keys = nullptr, *brick_chunk = nullptr;
-    unsigned int *d_counter = nullptr, *tops32 = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(f0); cudaFree(f1); cudaFree(rowmask); cudaFree(d_vals); cudaFree(d_keys); cudaFree(brick_chunk); cudaFree(d_counter); cudaFree(tops32);
-    };
+    c->incremental_ok = false;
+    uint8_t *f0 = nullptr, *f1 = nullptr;
+    auto cleanup = [&]() { cudaFree(f0); cudaFree(f1); };
 #define UVT_CUDA_C(expr)                                                                                      \
     do {                                                                                                      \
         cudaError_t e_ = (expr);                                                                              \
@@ -412,9 +458,10 @@ int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
                              #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
         }                                                                                                     \
     } while (0)
+    if (!c->d_scratch) UVT_CUDA_C(cudaMalloc(&c->d_scratch, kScratchWords * 4));
+    unsigned int *d_counter = reinterpret_cast<unsigned int *>(c->d_scratch + kScrFlags);
     UVT_CUDA_C(cudaMalloc(&f0, n_chunks));
     UVT_CUDA_C(cudaMalloc(&f1, n_chunks));
-    UVT_CUDA_C(cudaMalloc(&d_counter, 4));
     const unsigned cblocks = (unsigned)((n_chunks + 255) / 256);
     field_pass_x_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, cd);
     field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(f0, f1, cd, (size_t)cd);
@@ -425,58 +472,51 @@ int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
     UVT_CUDA_C(cudaMemcpyAsync(&n_virtual, d_counter, 4, cudaMemcpyDeviceToHost, c->stream));
     UVT_CUDA_C(cudaStreamSynchronize(c->stream));
     c->launches += 4;
-    const size_t n_total = n_bricks + n_virtual;
+    // spare real-brick slots below the virtual bricks, so that later edits can add bricks without renumbering
+    const size_t v_base = n_bricks + std::max<size_t>(256, n_bricks / 16);
+    const size_t n_total = v_base + n_virtual;
     if (n_total * 512 >= (1ull << 32)) {  // brick byte offsets are 32-bit in the traversal kernel
         cleanup();
         c->compact_ok = false;
         return UVT_OK;
     }
-    if (std::max<size_t>(n_total, 1) > c->d_brick8_capacity) {
-        cudaFree(c->d_bricks8);
-        c->d_bricks8 = nullptr;
-        const size_t want = std::max<size_t>(n_total + n_total / 4, 64);
+    if (n_total > c->d_brick8_capacity) {
+        cudaFree(c->d_bricks8); cudaFree(c->d_rowmask); cudaFree(c->d_brick_chunk);
+        c->d_bricks8 = nullptr; c->d_rowmask = nullptr; c->d_brick_chunk = nullptr;
+        c->d_brick8_capacity = 0;
+        const size_t want = std::min<size_t>(n_total + n_virtual / 4 + 256, ((1ull << 32) - 1) / 512);
         UVT_CUDA_C(cudaMalloc(&c->d_bricks8, want * 512));
+        UVT_CUDA_C(cudaMalloc(&c->d_rowmask, want * 64));
+        UVT_CUDA_C(cudaMalloc(&c->d_brick_chunk, want * 4));
         c->d_brick8_capacity = want;
     }
-    UVT_CUDA_C(cudaMalloc(&brick_chunk, std::max<size_t>(n_total, 1) * 4));
+    if (!c->d_tops32) UVT_CUDA_C(cudaMalloc(&c->d_tops32, (size_t)c->dim * c->dim * 4));
+    UVT_CUDA_C(cudaMemsetAsync(c->d_brick_chunk, 0xFF, c->d_brick8_capacity * 4, c->stream));  // kNoChunk
     UVT_CUDA_C(cudaMemsetAsync(d_counter, 0, 4, c->stream));
-    build_chunks2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(c->d_chunks, f0, c->d_chunks2, brick_chunk, cd, (uint32_t)n_bricks, d_counter);
+    build_chunks2_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(c->d_chunks, f0, c->d_chunks2, c->d_brick_chunk, cd, (uint32_t)v_base, d_counter);
     c->launches++;
-    UVT_CUDA_C(cudaMemsetAsync(c->d_clear4, 0, (size_t)(c->dim / 4) * (c->dim / 4) * 2, c->stream));  // empty world: nothing above y = 0
-    if (n_total) {
-        UVT_CUDA_C(cudaMemsetAsync(c->d_bricks8, 0, n_total * 512, c->stream));
+    UVT_CUDA_C(cudaMemsetAsync(c->d_bricks8, 0, n_total * 512, c->stream));
+    if (n_bricks) {
+        uint32_t *d_keys = c->d_scratch + kScrKeys;
+        uint8_t *d_vals = reinterpret_cast<uint8_t *>(c->d_scratch + kScrVals);
+        int rc = upload_material_lut(c, d_keys, d_vals);
+        if (rc != UVT_OK) { cleanup(); return rc; }
+        repack_bricks_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_bricks, c->d_bricks8, n_words, d_keys, d_vals, (uint32_t)kLutSize - 1);
+        c->launches++;
+    }
+    {   // column tops -> dilated 4x4 column-group tops (sky_sealed) -> y_clear
+        UVT_CUDA_C(cudaMemsetAsync(c->d_tops32, 0, (size_t)c->dim * c->dim * 4, c->stream));
         if (n_bricks) {
-            // open-addressed block word -> material id table for the repack kernel
-            const uint32_t lut_size = 1024, lut_mask = lut_size - 1;
-            std::vector<uint32_t> keys(lut_size, 0);
-            std::vector<uint8_t> vals(lut_size, 0);
-            for (size_t m = 1; m < c->mat_words.size(); ++m) {
-                uint32_t h = (c->mat_words[m] * 2654435761u) & lut_mask;
-                while (keys[h] != 0) h = (h + 1) & lut_mask;
-                keys[h] = c->mat_words[m];
-                vals[h] = (uint8_t)m;
-            }
-            UVT_CUDA_C(cudaMalloc(&d_keys, lut_size * 4));
-            UVT_CUDA_C(cudaMalloc(&d_vals, lut_size));
-            UVT_CUDA_C(cudaMemcpyAsync(d_keys, keys.data(), lut_size * 4, cudaMemcpyHostToDevice, c->stream));
-            UVT_CUDA_C(cudaMemcpyAsync(d_vals, vals.data(), lut_size, cudaMemcpyHostToDevice, c->stream));
-            repack_bricks_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_bricks, c->d_bricks8, n_words, d_keys, d_vals, lut_mask);
+            column_tops_kernel<<<(unsigned)n_bricks, 64, 0, c->stream>>>(c->d_bricks8, c->d_brick_chunk, cd, c->d_tops32);
             c->launches++;
-            UVT_CUDA_C(cudaStreamSynchronize(c->stream));  // keys/vals staging dies at scope exit
         }
-        {   // column tops -> dilated 4x4 column-group tops (sky_sealed)
-            const size_t ncol = (size_t)c->dim * c->dim;
-            UVT_CUDA_C(cudaMalloc(&tops32, ncol * 4));
-            UVT_CUDA_C(cudaMemsetAsync(tops32, 0, ncol * 4, c->stream));
-            if (n_bricks) column_tops_kernel<<<(unsigned)n_bricks, 64, 0, c->stream>>>(c->d_bricks8, brick_chunk, cd, tops32);
-            const int nq = (int)((c->dim / 4) * (c->dim / 4));
-            quad_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(tops32, c->d_clear4, (int)c->dim);
-            c->launches += 2;
-        }
-        UVT_CUDA_C(cudaMalloc(&rowmask, n_total * 64));
+        int rc = finish_tops(c, d_counter);
+        if (rc != UVT_OK) { cleanup(); return rc; }
+    }
+    {
         const size_t n_rows = n_total * 64;
-        brick_rowmask_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, c->stream>>>(c->d_bricks8, n_rows, rowmask);
-        clearance_kernel<<<(unsigned)n_total, 512, 0, c->stream>>>(c->d_chunks2, cd, brick_chunk, rowmask, c->d_bricks8);
+        brick_rowmask_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, c->stream>>>(c->d_bricks8, n_rows, c->d_rowmask);
+        clearance_kernel<<<(unsigned)n_total, 512, 0, c->stream>>>(c->d_chunks2, cd, c->d_brick_chunk, c->d_rowmask, c->d_bricks8);
         c->launches += 2;
     }
     // dense block grid (skipped when dim^3 bytes do not fit comfortably: the brick path is used instead)
@@ -500,6 +540,9 @@ int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
 #undef UVT_CUDA_C
     if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "building the compact layout failed: %s", cudaGetErrorString(e));
     c->n_total_bricks = n_total;
+    c->v_base = v_base;
+    c->n_virtual = n_virtual;
+    c->incremental_ok = true;
     return UVT_OK;
 }
 
@@ -582,6 +625,7 @@ void uvt_destroy(uvt_ctx *c) {
     free_gbuffer(c);
     cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
     cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
+    cudaFree(c->d_rowmask); cudaFree(c->d_brick_chunk); cudaFree(c->d_tops32); cudaFree(c->d_scratch);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
     cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame);
     for (int i = 0; i < 4; ++i)
@@ -676,8 +720,10 @@ int uvt_world_alloc(uvt_ctx *c, uint32_t dim, uint32_t **chunks_host, uint32_t *
     UVT_REQUIRE(c, brick_capacity > 0, "brick_capacity must be > 0");
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
-    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
+    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32);
     c->d_dense = nullptr;
+    c->d_tops32 = nullptr;
+    c->incremental_ok = false;
     c->dense_valid = false;
     c->h_chunks = c->h_bricks = nullptr;
     c->d_chunks = nullptr;
@@ -740,7 +786,7 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
     UVT_CUDA(c, cudaMemcpyAsync(c->d_chunks, c->h_chunks, n_chunks * 4, cudaMemcpyHostToDevice, c->stream));
     if (n_bricks) UVT_CUDA(c, cudaMemcpyAsync(c->d_bricks, c->h_bricks, n_bricks * 2048, cudaMemcpyHostToDevice, c->stream));
 
-    // material table: distinct block words in first-appearance order (deterministic)
+    // material table: the distinct block words, ascending
     c->mat_words.assign(1, 0u);
     std::unordered_map<uint32_t, uint32_t> ids;
     const size_t n_words = n_bricks * 512;
@@ -756,26 +802,10 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
             c->mat_words.push_back(wd);
         }
     }
+    std::sort(c->mat_words.begin() + 1, c->mat_words.end());  // canonical ids: the same materials always get the same ids
     c->compact_ok = !overflow;
+    c->incremental_ok = false;
     if (c->compact_ok) {
-        // highest occupied block row: chunk y of every brick + the highest non-empty local y inside it
-        int32_t top = -1;
-        const size_t cdz = c->cd;
-        for (size_t i = 0; i < n_chunks; ++i) {
-            const uint32_t e = c->h_chunks[i];
-            if (e == 0) continue;
-            const int32_t cy = (int32_t)((i / cdz) % cdz);
-            if (cy * 8 + 7 <= top) continue;
-            const uint32_t *bw = c->h_bricks + (size_t)(e - 1) * 512;
-            for (int ly = 7; ly >= 0 && cy * 8 + ly > top; --ly) {
-                bool any = false;
-                for (int lz = 0; lz < 8 && !any; ++lz)
-                    for (int lx = 0; lx < 8; ++lx)
-                        if (bw[lx + 8 * ly + 64 * lz] != 0) { any = true; break; }
-                if (any) { top = cy * 8 + ly; break; }
-            }
-        }
-        c->y_clear = top + 1;
         int rc = build_compact(c, n_bricks, n_words);
         if (rc != UVT_OK) return rc;
     }
@@ -783,6 +813,200 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
     c->n_bricks = n_bricks;
     c->world_committed = true;
     c->materials_dirty = true;
+    return UVT_OK;
+}
+
+// Incremental publish of a block box.  Everything a full commit derives from the edited
+// blocks is refreshed in place: the bricks of the box, the clearances and dense-grid bytes of every chunk
+// within two chunks of it (clearances look kClearCap = 16 blocks far), the column tops under it; a new brick
+// additionally refreshes the chunk distance field and gives newly adjacent empty chunks a virtual brick.
+int uvt_world_commit_region(uvt_ctx *c, size_t n_bricks, const uint32_t lo[3], const uint32_t hi[3]) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, c->h_chunks && c->h_bricks, "no world allocated");
+    UVT_REQUIRE(c, lo && hi, "NULL box");
+    UVT_REQUIRE(c, n_bricks <= c->h_capacity, "n_bricks exceeds the pool capacity");
+    for (int a = 0; a < 3; ++a) UVT_REQUIRE(c, lo[a] <= hi[a] && hi[a] < c->dim, "box must satisfy lo <= hi < dim");
+    const int cd = (int)c->cd;
+    const int o[3] = {(int)(lo[0] >> 3), (int)(lo[1] >> 3), (int)(lo[2] >> 3)};
+    const int bx = (int)(hi[0] >> 3) - o[0] + 1, by = (int)(hi[1] >> 3) - o[1] + 1, bz = (int)(hi[2] >> 3) - o[2] + 1;
+    const size_t nb = (size_t)bx * by * bz;
+    const size_t old_n = c->n_bricks;
+    // anything the in-place path cannot express is published by a full commit
+    if (!c->world_committed || !c->compact_ok || !c->incremental_ok || n_bricks < old_n || n_bricks > c->v_base ||
+        n_bricks > c->d_brick_capacity || nb > kMaxBoxChunks || n_bricks - old_n > kMaxListBricks / 2)
+        return uvt_world_commit(c, n_bricks);
+
+    // ---- host: box entries, bricks to refresh, new materials
+    std::vector<uint32_t> ents(nb), list;
+    for (int z = 0; z < bz; ++z)
+        for (int y = 0; y < by; ++y)
+            for (int x = 0; x < bx; ++x) {
+                const size_t j = (size_t)(o[0] + x) + (size_t)cd * ((size_t)(o[1] + y) + (size_t)(o[2] + z) * cd);
+                const uint32_t e = c->h_chunks[j];
+                if (e > n_bricks) return set_error(c, UVT_ERR_INVALID, "chunk entry %zu names brick %u >= n_bricks %zu", j, e - 1, n_bricks);
+                ents[(size_t)x + (size_t)bx * ((size_t)y + (size_t)by * z)] = e;
+                if (e != 0 && e - 1 < old_n) list.push_back(e - 1);
+            }
+    for (size_t b = old_n; b < n_bricks; ++b) list.push_back((uint32_t)b);
+    std::sort(list.begin(), list.end());
+    list.erase(std::unique(list.begin(), list.end()), list.end());
+    if (list.size() > kMaxListBricks) return uvt_world_commit(c, n_bricks);
+    bool new_materials = false;
+    for (uint32_t b : list) {
+        const uint32_t *bw = c->h_bricks + (size_t)b * 512;
+        uint32_t last_word = 0;
+        for (int i = 0; i < 512; ++i) {
+            const uint32_t wd = bw[i];
+            if (wd == 0 || wd == last_word) continue;
+            last_word = wd;
+            if (std::find(c->mat_words.begin() + 1, c->mat_words.end(), wd) == c->mat_words.end()) {
+                if (c->mat_words.size() >= kMatLimit) return uvt_world_commit(c, n_bricks);  // the full commit falls back to the reference layout
+                c->mat_words.push_back(wd);
+                new_materials = true;
+            }
+        }
+    }
+
+    // ---- uploads
+    uint32_t *d_ents = c->d_scratch + kScrEnts, *d_list = c->d_scratch + kScrList, *d_keys = c->d_scratch + kScrKeys;
+    uint8_t *d_vals = reinterpret_cast<uint8_t *>(c->d_scratch + kScrVals);
+    unsigned int *d_flags = reinterpret_cast<unsigned int *>(c->d_scratch + kScrFlags);
+    uint32_t *d_changed = c->d_scratch + kScrChanged;
+    for (uint32_t b : list)
+        UVT_CUDA(c, cudaMemcpyAsync(c->d_bricks + (size_t)b * 512, c->h_bricks + (size_t)b * 512, 2048, cudaMemcpyHostToDevice, c->stream));
+    UVT_CUDA(c, cudaMemcpyAsync(d_ents, ents.data(), nb * 4, cudaMemcpyHostToDevice, c->stream));
+    if (!list.empty()) UVT_CUDA(c, cudaMemcpyAsync(d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    UVT_CUDA(c, cudaMemsetAsync(d_flags, 0, 32, c->stream));
+    int rc = upload_material_lut(c, d_keys, d_vals);
+    if (rc != UVT_OK) return rc;
+
+    // ---- chunk entries and bricks
+    apply_chunk_box_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(c->d_chunks, d_ents, cd, o[0], o[1], o[2], bx, by, bz, d_flags + 0);
+    c->launches++;
+    if (!list.empty()) {
+        repack_list_kernel<<<(unsigned)list.size(), 64, 0, c->stream>>>(c->d_bricks, c->d_bricks8, c->d_rowmask, d_list, d_keys, d_vals, (uint32_t)kLutSize - 1);
+        c->launches++;
+    }
+    unsigned int table_changed = 0;
+    UVT_CUDA(c, cudaMemcpyAsync(&table_changed, d_flags + 0, 4, cudaMemcpyDeviceToHost, c->stream));
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_bricks = n_bricks;
+    if (new_materials) c->materials_dirty = true;
+
+    unsigned int n_changed = 0;
+    if (table_changed) {
+        // distance field -> new virtual bricks -> chunks2
+        const size_t n_chunks = (size_t)cd * cd * cd;
+        const unsigned cblocks = (unsigned)((n_chunks + 255) / 256);
+        uint8_t *f0 = nullptr, *f1 = nullptr;
+        if (cudaMalloc(&f0, n_chunks) != cudaSuccess || cudaMalloc(&f1, n_chunks) != cudaSuccess) {
+            cudaFree(f0); cudaFree(f1);
+            (void)cudaGetLastError();
+            return set_error(c, UVT_ERR_OOM, "no memory for the chunk distance field");
+        }
+        field_pass_x_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, cd);
+        field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(f0, f1, cd, (size_t)cd);
+        field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(f1, f0, cd, (size_t)cd * cd);
+        count_new_virtual_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, c->d_chunks2, cd, (uint32_t)c->v_base, d_flags + 1);
+        c->launches += 4;
+        unsigned int n_new = 0;
+        cudaError_t e = cudaMemcpyAsync(&n_new, d_flags + 1, 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess || c->v_base + c->n_virtual + n_new > c->d_brick8_capacity) {
+            cudaFree(f0); cudaFree(f1);
+            if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "distance field: %s", cudaGetErrorString(e));
+            return uvt_world_commit(c, n_bricks);  // out of virtual-brick slots: rebuild with fresh capacity
+        }
+        unsigned int nv = (unsigned int)c->n_virtual;
+        cudaMemcpyAsync(d_flags + 2, &nv, 4, cudaMemcpyHostToDevice, c->stream);
+        update_chunks2_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, c->d_chunks2, c->d_brick_chunk, c->d_bricks8, c->d_rowmask, cd,
+                                                              (uint32_t)c->v_base, d_flags + 2, d_changed, (uint32_t)kMaxChanged, d_flags + 3);
+        c->launches++;
+        unsigned int out[2] = {0, 0};
+        e = cudaMemcpyAsync(out, d_flags + 2, 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(f0); cudaFree(f1);
+        if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "chunks2 update: %s", cudaGetErrorString(e));
+        c->n_virtual = out[0];
+        c->n_total_bricks = c->v_base + c->n_virtual;
+        n_changed = out[1];
+    }
+
+    // ---- column tops under the box -> clear4 -> y_clear
+    UVT_CUDA(c, cudaMemset2DAsync(c->d_tops32 + (size_t)o[0] * 8 + (size_t)c->dim * ((size_t)o[2] * 8), (size_t)c->dim * 4, 0, (size_t)bx * 8 * 4,
+                                  (size_t)bz * 8, c->stream));
+    column_tops_box_kernel<<<dim3((unsigned)bx, (unsigned)cd, (unsigned)bz), 64, 0, c->stream>>>(c->d_chunks, c->d_bricks8, cd, o[0], o[2], c->d_tops32);
+    c->launches++;
+    rc = finish_tops(c, d_flags + 4);
+    if (rc != UVT_OK) return rc;
+
+    // ---- clearances and dense bytes of the box grown by two chunks
+    int g0[3], g1[3];
+    const int ext[3] = {bx, by, bz};
+    for (int a = 0; a < 3; ++a) {
+        g0[a] = std::max(o[a] - 2, 0);
+        g1[a] = std::min(o[a] + ext[a] - 1 + 2, cd - 1);
+    }
+    const dim3 ggrid((unsigned)(g1[0] - g0[0] + 1), (unsigned)(g1[1] - g0[1] + 1), (unsigned)(g1[2] - g0[2] + 1));
+    clearance_box_kernel<<<ggrid, 512, 0, c->stream>>>(c->d_chunks2, cd, g0[0], g0[1], g0[2], c->d_rowmask, c->d_bricks8);
+    c->launches++;
+    if (c->d_dense && c->dense_valid) {
+        if (n_changed > kMaxChanged) {
+            dense_fill_kernel<<<(unsigned)((size_t)cd * cd * cd), 64, 0, c->stream>>>(c->d_chunks2, c->d_bricks8, c->d_dense, cd);
+        } else {
+            dense_fill_box_kernel<<<ggrid, 64, 0, c->stream>>>(c->d_chunks2, c->d_bricks8, c->d_dense, cd, g0[0], g0[1], g0[2]);
+            if (n_changed) {
+                dense_fill_list_kernel<<<n_changed, 64, 0, c->stream>>>(c->d_chunks2, c->d_bricks8, c->d_dense, cd, d_changed);
+                c->launches++;
+            }
+        }
+        c->launches++;
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        c->incremental_ok = false;
+        return set_error(c, UVT_ERR_CUDA, "incremental commit failed: %s", cudaGetErrorString(e));
+    }
+    return UVT_OK;
+}
+
+// map_setVoxel (map.glsl:49-55): the write lands only where the chunk already holds a brick
+int uvt_world_set_voxel(uvt_ctx *c, uint32_t x, uint32_t y, uint32_t z, uint32_t voxel, int *written) {
+    if (!c) return UVT_ERR_INVALID;
+    if (written) *written = 0;
+    UVT_REQUIRE(c, c->h_chunks && c->h_bricks && c->world_committed, "no world committed");
+    if (x >= c->dim || y >= c->dim || z >= c->dim) return UVT_OK;  // map_getChunkFlags reads 0 outside the map
+    const uint32_t e = c->h_chunks[(size_t)(x >> 3) + (size_t)c->cd * ((size_t)(y >> 3) + (size_t)(z >> 3) * c->cd)];
+    if (e == 0 || e > c->n_bricks) return UVT_OK;
+    c->h_bricks[(size_t)(e - 1) * 512 + (x & 7u) + 8u * (y & 7u) + 64u * (z & 7u)] = voxel;
+    if (written) *written = 1;
+    const uint32_t p[3] = {x, y, z};
+    return uvt_world_commit_region(c, c->n_bricks, p, p);
+}
+
+int uvt_world_layout_checksum(uvt_ctx *c, uint64_t out[4]) {
+    if (!c || !out) return UVT_ERR_INVALID;
+    UVT_REQUIRE(c, c->world_committed, "no world committed");
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (!c->compact_ok) return UVT_OK;  // reference layout only: nothing derived
+    int rc = ensure_ready(c);            // material tables
+    if (rc != UVT_OK) return rc;
+    unsigned long long *d = nullptr;
+    UVT_CUDA(c, cudaMalloc(&d, 32));
+    cudaMemsetAsync(d, 0, 32, c->stream);
+    const int cd = (int)c->cd;
+    const int nq = (int)((c->dim / 4) * (c->dim / 4));
+    layout_checksum_kernel<<<(unsigned)((size_t)cd * cd * cd), 64, 0, c->stream>>>(c->d_chunks2, c->d_bricks8, c->dense_valid ? c->d_dense : nullptr, c->d_mat_word, cd, d);
+    clear4_checksum_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, nq, d);
+    c->launches += 2;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, d, 32, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "layout checksum: %s", cudaGetErrorString(e));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    out[3] = (uint64_t)(uint32_t)c->y_clear | ((uint64_t)(c->mat_words.size() - 1) << 32);
     return UVT_OK;
 }
 

@@ -130,6 +130,18 @@ class Context:
     def dispatch_frame(self):
         self.check(self.L.uvt_dispatch_frame(self.handle))
 
+    def world_set_voxel(self, x, y, z, voxel):
+        """map_setVoxel (map.glsl:49-55): write + publish one block; False where the chunk holds no brick."""
+        w = ctypes.c_int(0)
+        self.check(self.L.uvt_world_set_voxel(self.handle, x, y, z, voxel, ctypes.byref(w)))
+        return bool(w.value)
+
+    def world_layout_checksum(self):
+        out = (ctypes.c_uint64 * 4)()
+        self.check(self.L.uvt_world_layout_checksum(self.handle, ctypes.byref(out)))
+        d, b, q, m = (int(v) for v in out)
+        return d, b, q, m & 0xFFFFFFFF, m >> 32   # dense, bricks, clear4, y_clear, n_materials
+
     def sync(self):
         self.check(self.L.uvt_sync(self.handle))
 

@@ -80,19 +80,28 @@ class VoxelBrickmap:
         return int(self._L.uvt_brickmap_capacity(self.handle))
 
     def chunks(self):
-        """numpy view of the chunk table u32[(dim/8)^3] (no copy)."""
+        """read-only numpy view of the chunk table u32[(dim/8)^3] (no copy; writes go through set())."""
         n = (self.dim // 8) ** 3
         p = self._L.uvt_brickmap_chunks(self.handle)
-        return np.ctypeslib.as_array((ctypes.c_uint32 * n).from_address(p))
+        a = np.ctypeslib.as_array((ctypes.c_uint32 * n).from_address(p))
+        a.flags.writeable = False
+        return a
 
     def bricks(self):
-        """numpy view of the committed part of the brick pool u32[n_bricks][512] (no copy)."""
+        """read-only numpy view of the committed part of the brick pool u32[n_bricks][512] (no copy)."""
         n = max(self.n_bricks, 1) * 512
         p = self._L.uvt_brickmap_bricks(self.handle)
-        return np.ctypeslib.as_array((ctypes.c_uint32 * n).from_address(p)).reshape(-1, 512)
+        a = np.ctypeslib.as_array((ctypes.c_uint32 * n).from_address(p)).reshape(-1, 512)
+        a.flags.writeable = False
+        return a
+
+    def mark_dirty(self):
+        """After writes that bypassed set(): the next bind() republishes the whole map."""
+        self._L.uvt_brickmap_mark_dirty(self.handle)
 
     def bind(self, base_binding=9):
-        """voxel.zig:77-80: pool -> binding 9, chunk table -> binding 10."""
+        """voxel.zig:77-80: pool -> binding 9, chunk table -> binding 10.  Publishes what set() wrote since the last
+        bind (first bind: everything; clean map: nothing), so calling it every frame like game.zig:236 is cheap."""
         if base_binding != 9:
             raise UvtError(N.UVT_ERR_INVALID, "voxelData/mapData are bindings 9/10 (map.glsl:11-17)")
         if not self.ctx:
