@@ -450,7 +450,9 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
             if (simple && !seals) {
                 limit = lim0;
                 slow = false;
+#ifndef UVT_ROUND_STATS
                 if (COUNT == 2) tc.t_in++;
+#endif
             }
         }
         if (slow) {
@@ -460,7 +462,9 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
                 out.px = out.py = out.pz = 0xFFFFFFFFu;
                 limit = kDead;
             } else {
+#ifndef UVT_ROUND_STATS
                 if (COUNT == 2) tc.t_in++;  // lookups performed
+#endif
                 uint32_t px = (uint32_t)gx, py = (uint32_t)gy, pz = (uint32_t)gz;
                 uint32_t mat;
                 int n_free = 0;
@@ -563,6 +567,17 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
         // live lanes: 1 <= limit - trip (limit is clamped to max_steps > trip); parked lanes: huge
         int k = __reduce_min_sync(0xFFFFFFFFu, limit - trip);
         if (k >= kDead / 2) break;  // no live lane left
+#ifdef UVT_ROUND_STATS
+        if (COUNT == 2) {  // experiment build: t_in = rounds, t_chunk = single-trip rounds forced by a sub-voxel lane, t_block = by a block-step lane
+            const bool lim1 = limit - trip == 1;
+            const unsigned sub = __ballot_sync(0xFFFFFFFFu, lim1 && !big), blk = __ballot_sync(0xFFFFFFFFu, lim1 && big);
+            if ((threadIdx.x & 31u) == 0) {
+                tc.t_in++;
+                if (sub) tc.t_chunk++;
+                else if (blk) tc.t_block++;
+            }
+        }
+#endif
         k = min(k, seg_end - trip);  // warp-uniform; >= 1
 
         // ---- k DDA steps, branch-free (map.glsl:157-162) -----------------------------------
