@@ -143,6 +143,10 @@ int  uvt_pipeline_dispatch(uvt_pipeline *p, uint32_t gx, uint32_t gy, uint32_t g
  * (chunks: u32[(dim/8)^3], 0 = empty else brick+1; bricks: u32[capacity][512],
  * index x%8 + 8*(y%8) + 64*(z%8)); uvt_world_commit() uploads and repacks it. */
 int  uvt_world_alloc(uvt_ctx *ctx, uint32_t dim, uint32_t **chunks_host, uint32_t **bricks_host, size_t brick_capacity);
+/* The same with CALLER-OWNED staging (the host keeps its own chunk table and brick pool, same layout; pinned memory
+ * uploads asynchronously, pageable memory works too).  dim = 0 afterwards re-points the brick pool after the caller
+ * grew or moved it (chunks_host is ignored).  The ctx never frees these; uvt_world_grow is refused. */
+int  uvt_world_use_staging(uvt_ctx *ctx, uint32_t dim, uint32_t *chunks_host, uint32_t *bricks_host, size_t brick_capacity);
 /* GpuBlockAllocator.alloc growth (gpu_block_allocator.zig:20-24 → buffer.zig:48-62): contents are preserved. */
 int  uvt_world_grow(uvt_ctx *ctx, size_t new_capacity, uint32_t **bricks_host);
 /* Make host edits visible to the GPU (H2D + repack kernel). n_bricks = GpuBlockAllocator.block_index. */
@@ -242,6 +246,31 @@ uint64_t uvt_launch_count(uvt_ctx *ctx);
  * repeatedly reads an L2-resident buffer of `bytes` with 16-B loads; returns GB/s. */
 int  uvt_measure_l2_read_gbps(uvt_ctx *ctx, size_t bytes, int repeats, float *gbps);
 int  uvt_measure_hbm_copy_gbps(uvt_ctx *ctx, size_t bytes, int repeats, float *gbps);
+
+/* ---- several GPUs in ONE process (the reference is a single-process game, src/game.zig) ----------
+ * A group owns one ctx per device.  World and atlas are replicated from one pinned staging; the frame is cut into
+ * interleaved 32-row bands (member i renders bands i, i+n, ...) and every member's kernels store their finished
+ * bands straight into the frame of member 0 over NVLink (peer access) — no gather pass.  Calls mirror the ctx calls
+ * and fan out to every member; uvt_group_member(g, 0) presents (uvt_pick, timing, ...).  With n = 1 the group is a
+ * plain ctx.  Only the FRAME is assembled; the G-buffers stay partitioned on their devices. */
+typedef struct uvt_group uvt_group;
+int  uvt_group_create(const uvt_params *params, const int *devices, int n, uvt_group **out);
+void uvt_group_destroy(uvt_group *g);
+int  uvt_group_size(const uvt_group *g);
+uvt_ctx *uvt_group_member(uvt_group *g, int i);
+const char *uvt_group_last_error(uvt_group *g);        /* g may be NULL after a failed create */
+int  uvt_group_world_alloc(uvt_group *g, uint32_t dim, uint32_t **chunks_host, uint32_t **bricks_host, size_t brick_capacity);
+int  uvt_group_world_grow(uvt_group *g, size_t new_capacity, uint32_t **bricks_host);
+int  uvt_group_world_commit(uvt_group *g, size_t n_bricks);
+int  uvt_group_world_commit_region(uvt_group *g, size_t n_bricks, const uint32_t lo[3], const uint32_t hi[3]);
+int  uvt_group_atlas_upload(uvt_group *g, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t w, uint32_t h, uint32_t d, const uint32_t *rgba);
+int  uvt_group_set_camera(uvt_group *g, const uvt_camera *cam);
+int  uvt_group_resize(uvt_group *g, uint32_t width, uint32_t height);
+int  uvt_group_dispatch_frame(uvt_group *g);           /* primary + secondary + shade on every member, asynchronous */
+int  uvt_group_sync(uvt_group *g);
+int  uvt_group_readback_frame(uvt_group *g, void *dst, size_t bytes);   /* waits for every member, W*H*4 bytes */
+int  uvt_group_frame_ptr(uvt_group *g, void **dptr);   /* the assembled frame on member 0's device (interop) */
+int  uvt_group_count_pass(uvt_group *g, int which, uvt_counters *sum);  /* uvt_count_pass summed over the members */
 
 #ifdef __cplusplus
 }

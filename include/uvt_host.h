@@ -35,6 +35,8 @@ typedef struct uvt_brickmap uvt_brickmap;
 /* ctx may be NULL (plain host memory).  Initial pool capacity = dim bricks
  * (GpuBlockAllocator.init(dim), voxel.zig:36), doubling on exhaustion. */
 int      uvt_brickmap_create(uvt_ctx *ctx, uint32_t dim, uvt_brickmap **out);
+/* The same over a multi-GPU group (uvt.h, uvt_group): one staging, bind() publishes to every member. */
+int      uvt_brickmap_create_group(uvt_group *group, uint32_t dim, uvt_brickmap **out);
 void     uvt_brickmap_destroy(uvt_brickmap *bm);
 void     uvt_brickmap_clear(uvt_brickmap *bm);                                /* voxel.zig:41-44 */
 int      uvt_brickmap_set(uvt_brickmap *bm, uint32_t x, uint32_t y, uint32_t z, uint32_t voxel); /* :58-61 */
@@ -79,6 +81,7 @@ const char *uvt_vox_error(void);
 /* ---- VoxelModelAtlas: src/engine/voxel.zig:84-132 ------------------------------------ */
 typedef struct uvt_atlas uvt_atlas;
 int      uvt_atlas_create(uvt_ctx *ctx, uvt_atlas **out);       /* 256^3 RGBA8 (voxel.zig:88-92); ctx may be NULL */
+int      uvt_atlas_create_group(uvt_group *group, uvt_atlas **out);   /* models are uploaded to every member */
 void     uvt_atlas_destroy(uvt_atlas *a);
 /* load_block_model (voxel.zig:115-127): every model of the file → next slots, y/z swapped. */
 int      uvt_atlas_load_block_model(uvt_atlas *a, const char *path);

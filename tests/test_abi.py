@@ -63,3 +63,19 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "oracle/" not in text.replace("the oracle/", ""), f
+
+
+def test_group_create_fails_loudly_without_a_gpu():
+    import ctypes
+    import importlib
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present")
+    uvt = importlib.import_module("unnamed-voxel-tracer_b200")
+    L = uvt._native.load()
+    devs = (ctypes.c_int * 2)(0, 1)
+    h = ctypes.c_void_p()
+    rc = L.uvt_group_create(None, devs, 2, ctypes.byref(h))
+    assert rc == uvt._native.UVT_ERR_NO_DEVICE and not h.value
+    assert b"no CPU path" in L.uvt_group_last_error(None)

@@ -645,3 +645,69 @@ def test_incremental_commit_on_w1_near_camera(uvt, oracle, scene_factory):
         ref = gpu_render(ctx, cam)
         ctx.set_layout("compact")
         _same_render(gpu_render(ctx, cam), ref)
+
+
+# ---- several GPUs in one process (uvt_group): members may share a device, so one GPU is enough to test the plumbing ----
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0]])
+def test_group_frame_equals_single_ctx(uvt, oracle, scene_factory, devices):
+    cam = camera_k1(uvt, oracle)
+    with uvt.Context(0) as ctx, uvt.Group(devices) as grp:
+        sc1 = scene_factory(512, "procgen", ctx=ctx)
+        scene_factory(512, "procgen", ctx=grp)
+        assert grp.size == len(devices)
+        for (W, H) in ((320, 200), (1920, 1080)):   # 200 rows: a ragged last band
+            ctx.resize(W, H)
+            ctx.set_camera(cam)
+            ctx.dispatch_frame()
+            ref = ctx.readback("frame")
+            grp.resize(W, H)
+            grp.set_camera(cam)
+            grp.dispatch_frame()
+            got = grp.readback_frame()
+            assert np.array_equal(got, ref)
+            for which in ("primary", "secondary"):
+                assert grp.count_pass(which) == ctx.count_pass(which)
+        r = oracle.render(sc1.oracle_world, cam, 320, 200)
+        grp.resize(320, 200)
+        grp.dispatch_frame()
+        assert channel_diff(grp.readback_frame(), r["frame"]).max() <= 1
+
+
+def test_group_world_edits_reach_every_member(uvt, oracle, scene_factory):
+    V = uvt.voxel.Voxel
+    cam = camera_k0(oracle)
+    with uvt.Context(0) as ctx, uvt.Group([0, 0]) as grp:
+        a = scene_factory(512, "procgen", ctx=ctx)
+        b = scene_factory(512, "procgen", ctx=grp)
+        for c in (ctx, grp):
+            c.resize(320, 192)
+            c.set_camera(cam)
+        for step in range(3):
+            for sc in (a, b):
+                for y in range(20, 30 + 4 * step):
+                    for x in range(250, 262):
+                        sc.bm.set(x, y, 268 + step, V(11, True))    # walls in front of the camera: new bricks, both bands
+                sc.bm.bind(9)
+            ctx.dispatch_frame()
+            grp.dispatch_frame()
+            assert np.array_equal(grp.readback_frame(), ctx.readback("frame")), step
+
+
+def test_group_across_two_gpus(uvt, oracle, scene_factory):
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    cam = camera_k1(uvt, oracle)
+    with uvt.Context(0) as ctx, uvt.Group(list(range(_n_gpus()))) as grp:
+        scene_factory(512, "procgen", ctx=ctx)
+        scene_factory(512, "procgen", ctx=grp)
+        for c in (ctx, grp):
+            c.resize(1920, 1080)
+            c.set_camera(cam)
+        ctx.dispatch_frame()
+        grp.dispatch_frame()
+        assert np.array_equal(grp.readback_frame(), ctx.readback("frame"))

@@ -5,6 +5,6 @@ ABI of include/uvt.h; this package is the Python mirror of the reference's host 
 library and a B200 every dispatch raises.
 """
 from . import _native, build, gfx, voxel, procgen, game, tiles, scenes  # noqa: F401
-from .gfx import Context, UvtError, init  # noqa: F401
+from .gfx import Context, Group, UvtError, init  # noqa: F401
 
-__all__ = ["gfx", "voxel", "procgen", "game", "tiles", "scenes", "Context", "UvtError", "init", "build"]
+__all__ = ["gfx", "voxel", "procgen", "game", "tiles", "scenes", "Context", "Group", "UvtError", "init", "build"]

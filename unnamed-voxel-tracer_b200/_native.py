@@ -65,6 +65,7 @@ SIGNATURES = {
     "uvt_pipeline_destroy": (None, [c_p]),
     "uvt_pipeline_dispatch": (c_int, [c_p, c_u32, c_u32, c_u32]),
     "uvt_world_alloc": (c_int, [c_p, c_u32, P(c_p), P(c_p), c_size]),
+    "uvt_world_use_staging": (c_int, [c_p, c_u32, c_p, c_p, c_size]),
     "uvt_world_grow": (c_int, [c_p, c_size, P(c_p)]),
     "uvt_world_commit": (c_int, [c_p, c_size]),
     "uvt_world_commit_region": (c_int, [c_p, c_size, P(c_u32 * 3), P(c_u32 * 3)]),
@@ -101,8 +102,26 @@ SIGNATURES = {
     "uvt_launch_count": (ctypes.c_uint64, [c_p]),
     "uvt_measure_l2_read_gbps": (c_int, [c_p, c_size, c_int, P(c_f)]),
     "uvt_measure_hbm_copy_gbps": (c_int, [c_p, c_size, c_int, P(c_f)]),
+    "uvt_group_create": (c_int, [P(Params), P(c_int), c_int, P(c_p)]),
+    "uvt_group_destroy": (None, [c_p]),
+    "uvt_group_size": (c_int, [c_p]),
+    "uvt_group_member": (c_p, [c_p, c_int]),
+    "uvt_group_last_error": (ctypes.c_char_p, [c_p]),
+    "uvt_group_world_alloc": (c_int, [c_p, c_u32, P(c_p), P(c_p), c_size]),
+    "uvt_group_world_grow": (c_int, [c_p, c_size, P(c_p)]),
+    "uvt_group_world_commit": (c_int, [c_p, c_size]),
+    "uvt_group_world_commit_region": (c_int, [c_p, c_size, P(c_u32 * 3), P(c_u32 * 3)]),
+    "uvt_group_atlas_upload": (c_int, [c_p, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, c_p]),
+    "uvt_group_set_camera": (c_int, [c_p, c_p]),
+    "uvt_group_resize": (c_int, [c_p, c_u32, c_u32]),
+    "uvt_group_dispatch_frame": (c_int, [c_p]),
+    "uvt_group_sync": (c_int, [c_p]),
+    "uvt_group_readback_frame": (c_int, [c_p, c_p, c_size]),
+    "uvt_group_frame_ptr": (c_int, [c_p, P(c_p)]),
+    "uvt_group_count_pass": (c_int, [c_p, c_int, P(Counters)]),
     # uvt_host.h
     "uvt_brickmap_create": (c_int, [c_p, c_u32, P(c_p)]),
+    "uvt_brickmap_create_group": (c_int, [c_p, c_u32, P(c_p)]),
     "uvt_brickmap_destroy": (None, [c_p]),
     "uvt_brickmap_clear": (None, [c_p]),
     "uvt_brickmap_set": (c_int, [c_p, c_u32, c_u32, c_u32, c_u32]),
@@ -130,6 +149,7 @@ SIGNATURES = {
     "uvt_vox_palette": (c_p, [c_p]),
     "uvt_vox_error": (ctypes.c_char_p, []),
     "uvt_atlas_create": (c_int, [c_p, P(c_p)]),
+    "uvt_atlas_create_group": (c_int, [c_p, P(c_p)]),
     "uvt_atlas_destroy": (None, [c_p]),
     "uvt_atlas_load_block_model": (c_int, [c_p, ctypes.c_char_p]),
     "uvt_atlas_load_block_model_mem": (c_int, [c_p, c_p, c_size]),

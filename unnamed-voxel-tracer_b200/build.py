@@ -14,6 +14,7 @@ LIB = os.path.join(HERE, "libuvt.so")
 
 SOURCES = [
     os.path.join(CSRC, "uvt.cu"),
+    os.path.join(CSRC, "group.cpp"),
     os.path.join(CSRC, "host", "noise.cpp"),
     os.path.join(CSRC, "host", "world.cpp"),
     os.path.join(CSRC, "host", "vox.cpp"),

@@ -14,6 +14,7 @@
 
 struct uvt_atlas {
     uvt_ctx *ctx = nullptr;
+    uvt_group *group = nullptr;
     size_t current_index = 0;  // voxel.zig:86
     std::vector<std::array<uint32_t, 512>> models;
 };
@@ -24,8 +25,9 @@ int push_model(uvt_atlas *a, const uint32_t texels[512]) {
     const size_t idx = a->current_index;
     const size_t base_x = idx % 32, base_y = (idx / 32) % 32, base_z = (idx / 1024) % 1024;
     if (base_z >= 32) return UVT_ERR_INVALID;  // outside the 256^3 texture (a GL error in the reference)
-    if (a->ctx) {
-        int rc = uvt_atlas_upload(a->ctx, (uint32_t)base_x * 8, (uint32_t)base_y * 8, (uint32_t)base_z * 8, 8, 8, 8, texels);
+    if (a->ctx || a->group) {
+        int rc = a->group ? uvt_group_atlas_upload(a->group, (uint32_t)base_x * 8, (uint32_t)base_y * 8, (uint32_t)base_z * 8, 8, 8, 8, texels)
+                          : uvt_atlas_upload(a->ctx, (uint32_t)base_x * 8, (uint32_t)base_y * 8, (uint32_t)base_z * 8, 8, 8, 8, texels);
         if (rc != UVT_OK) return rc;
     }
     std::array<uint32_t, 512> m;
@@ -68,6 +70,14 @@ int uvt_atlas_create(uvt_ctx *ctx, uvt_atlas **out) {
     if (!out) return UVT_ERR_INVALID;
     uvt_atlas *a = new uvt_atlas;
     a->ctx = ctx;
+    *out = a;
+    return UVT_OK;
+}
+
+int uvt_atlas_create_group(uvt_group *group, uvt_atlas **out) {
+    if (!out || !group) return UVT_ERR_INVALID;
+    uvt_atlas *a = new uvt_atlas;
+    a->group = group;
     *out = a;
     return UVT_OK;
 }

@@ -14,6 +14,7 @@
 
 struct uvt_brickmap {
     uvt_ctx *ctx = nullptr;
+    uvt_group *group = nullptr;  // attached to a multi-GPU group instead of one ctx (ctx = its member 0)
     uint32_t dim = 0;       // blocks per axis
     uint32_t cdim = 0;      // chunks per axis = dim / 8
     uint32_t *chunks = nullptr;
@@ -38,7 +39,7 @@ int brick_alloc(uvt_brickmap *bm, size_t *out) {
         size_t new_cap = bm->max_block_index * 2;
         if (bm->ctx) {
             uint32_t *nb = nullptr;
-            int rc = uvt_world_grow(bm->ctx, new_cap, &nb);
+            int rc = bm->group ? uvt_group_world_grow(bm->group, new_cap, &nb) : uvt_world_grow(bm->ctx, new_cap, &nb);
             if (rc != UVT_OK) return rc;
             bm->bricks = nb;
         } else {
@@ -75,17 +76,27 @@ int block_for_chunk(uvt_brickmap *bm, size_t chx, size_t chy, size_t chz, size_t
 
 extern "C" {
 
-int uvt_brickmap_create(uvt_ctx *ctx, uint32_t dim, uvt_brickmap **out) {
+static int brickmap_create(uvt_ctx *ctx, uvt_group *group, uint32_t dim, uvt_brickmap **out);
+
+int uvt_brickmap_create(uvt_ctx *ctx, uint32_t dim, uvt_brickmap **out) { return brickmap_create(ctx, nullptr, dim, out); }
+
+int uvt_brickmap_create_group(uvt_group *group, uint32_t dim, uvt_brickmap **out) {
+    if (!group) return UVT_ERR_INVALID;
+    return brickmap_create(uvt_group_member(group, 0), group, dim, out);
+}
+
+static int brickmap_create(uvt_ctx *ctx, uvt_group *group, uint32_t dim, uvt_brickmap **out) {
     if (!out || dim == 0 || dim % kChunk != 0) return UVT_ERR_INVALID;
     uvt_brickmap *bm = new (std::nothrow) uvt_brickmap;
     if (!bm) return UVT_ERR_OOM;
     bm->ctx = ctx;
+    bm->group = group;
     bm->dim = dim;
     bm->cdim = dim / kChunk;
     const size_t n_chunks = (size_t)bm->cdim * bm->cdim * bm->cdim;
     const size_t cap = dim;  // GpuBlockAllocator.init(dim): voxel.zig:36
     if (ctx) {
-        int rc = uvt_world_alloc(ctx, dim, &bm->chunks, &bm->bricks, cap);
+        int rc = group ? uvt_group_world_alloc(group, dim, &bm->chunks, &bm->bricks, cap) : uvt_world_alloc(ctx, dim, &bm->chunks, &bm->bricks, cap);
         if (rc != UVT_OK) { delete bm; return rc; }
     } else {
         bm->chunks = (uint32_t *)std::calloc(n_chunks, sizeof(uint32_t));
@@ -152,8 +163,11 @@ int uvt_brickmap_bind(uvt_brickmap *bm) {
     if (!bm->ctx) return UVT_ERR_INVALID;
     // the reference's mapping is live and bind() is a per-frame GL call (game.zig:236): publish only what was written
     int rc = UVT_OK;
-    if (!bm->bound || bm->dirty_all) rc = uvt_world_commit(bm->ctx, bm->block_index);
-    else if (bm->dirty) rc = uvt_world_commit_region(bm->ctx, bm->block_index, bm->dirty_lo, bm->dirty_hi);
+    if (!bm->bound || bm->dirty_all)
+        rc = bm->group ? uvt_group_world_commit(bm->group, bm->block_index) : uvt_world_commit(bm->ctx, bm->block_index);
+    else if (bm->dirty)
+        rc = bm->group ? uvt_group_world_commit_region(bm->group, bm->block_index, bm->dirty_lo, bm->dirty_hi)
+                       : uvt_world_commit_region(bm->ctx, bm->block_index, bm->dirty_lo, bm->dirty_hi);
     if (rc != UVT_OK) return rc;
     bm->bound = true;
     bm->dirty = bm->dirty_all = false;

@@ -42,6 +42,7 @@ struct uvt_ctx {
     uint32_t *h_chunks = nullptr;
     uint32_t *h_bricks = nullptr;
     size_t h_capacity = 0;  // bricks
+    bool staging_borrowed = false;  // h_chunks / h_bricks belong to the caller (uvt_world_use_staging)
     size_t n_bricks = 0;    // committed
     uint32_t *d_chunks = nullptr;
     uint32_t *d_bricks = nullptr;
@@ -137,6 +138,13 @@ int set_error(uvt_ctx *ctx, int code, const char *fmt, ...) {
         if (e_ != cudaSuccess)                                                                                  \
             return set_error((ctx), e_ == cudaErrorMemoryAllocation ? UVT_ERR_OOM : UVT_ERR_CUDA, "%s: %s (%s:%d)", \
                              #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                                \
+    } while (0)
+
+// several ctxs on different devices may live in one thread (uvt_group): every entry point selects its device
+#define UVT_ENTER(ctx)                                  \
+    do {                                                \
+        int cur_ = -1;                                  \
+        if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != (ctx)->device) cudaSetDevice((ctx)->device); \
     } while (0)
 
 #define UVT_REQUIRE(ctx, cond, msg)                                  \
@@ -623,7 +631,7 @@ void uvt_destroy(uvt_ctx *c) {
         if (c->snap_done[i]) cudaEventDestroy(c->snap_done[i]);
     }
     free_gbuffer(c);
-    cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
+    if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
     cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
     cudaFree(c->d_rowmask); cudaFree(c->d_brick_chunk); cudaFree(c->d_tops32); cudaFree(c->d_scratch);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
@@ -639,6 +647,7 @@ const char *uvt_last_error(uvt_ctx *ctx) { return ctx ? ctx->error.c_str() : g_c
 
 int uvt_set_stream(uvt_ctx *c, void *cuda_stream) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
     return UVT_OK;
@@ -652,6 +661,7 @@ int uvt_get_params(uvt_ctx *c, uvt_params *out) {
 
 int uvt_set_layout(uvt_ctx *c, uint32_t layout) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, layout == UVT_LAYOUT_COMPACT || layout == UVT_LAYOUT_REFERENCE, "unknown layout");
     c->params.layout = layout;
     return UVT_OK;
@@ -659,6 +669,7 @@ int uvt_set_layout(uvt_ctx *c, uint32_t layout) {
 
 int uvt_set_scheduler(uvt_ctx *c, uint32_t scheduler) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, scheduler == UVT_SCHED_POOL || scheduler == UVT_SCHED_TILE, "unknown scheduler");
     c->params.scheduler = scheduler;
     return UVT_OK;
@@ -666,11 +677,13 @@ int uvt_set_scheduler(uvt_ctx *c, uint32_t scheduler) {
 
 int uvt_effective_layout(uvt_ctx *c) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     return use_compact(c) ? (int)UVT_LAYOUT_COMPACT : (int)UVT_LAYOUT_REFERENCE;
 }
 
 int uvt_set_max_steps(uvt_ctx *c, uint32_t primary, uint32_t shadow) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, primary <= 65535u && shadow <= 65535u, "step caps must fit 16 bits (uvt_hit.trips)");
     c->params.primary_max_steps = primary;
     c->params.shadow_max_steps = shadow;
@@ -680,6 +693,7 @@ int uvt_set_max_steps(uvt_ctx *c, uint32_t primary, uint32_t shadow) {
 // ---- pipelines -----------------------------------------------------------------------------
 int uvt_pipeline_create(uvt_ctx *c, uvt_pipeline_kind kind, uvt_pipeline **out) {
     if (!c || !out) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, kind >= UVT_PIPELINE_PRIMARY && kind <= UVT_PIPELINE_BLIT, "unknown pipeline kind");
     // the analogue of compile + link: make sure the kernel image for this device resolves
     cudaFuncAttributes fa;
@@ -713,49 +727,85 @@ int uvt_pipeline_dispatch(uvt_pipeline *p, uint32_t gx, uint32_t gy, uint32_t gz
 }
 
 // ---- world ------------------------------------------------------------------------------------
-int uvt_world_alloc(uvt_ctx *c, uint32_t dim, uint32_t **chunks_host, uint32_t **bricks_host, size_t brick_capacity) {
-    if (!c) return UVT_ERR_INVALID;
-    UVT_REQUIRE(c, chunks_host && bricks_host, "NULL out pointer");
-    UVT_REQUIRE(c, dim >= 8 && dim % 8 == 0 && dim <= 4096, "dim must be a multiple of 8 in [8, 4096]");
-    UVT_REQUIRE(c, brick_capacity > 0, "brick_capacity must be > 0");
+// drop the current world and size the device-side tables for `dim` (host staging is set by the caller)
+static int reset_world(uvt_ctx *c, uint32_t dim) {
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks);
+    if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
     cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32);
     c->d_dense = nullptr;
     c->d_tops32 = nullptr;
     c->incremental_ok = false;
     c->dense_valid = false;
     c->h_chunks = c->h_bricks = nullptr;
+    c->staging_borrowed = false;
     c->d_chunks = nullptr;
     c->d_chunks2 = nullptr;
     c->d_clear4 = nullptr;
     c->dim = dim;
     c->cd = dim / 8;
     c->params.map_dim = dim;
+    c->h_capacity = 0;
+    c->n_bricks = 0;
+    c->world_committed = false;
     const size_t n_chunks = (size_t)c->cd * c->cd * c->cd;
-    UVT_CUDA(c, cudaHostAlloc(&c->h_chunks, n_chunks * 4, cudaHostAllocDefault));
-    UVT_CUDA(c, cudaHostAlloc(&c->h_bricks, brick_capacity * 2048, cudaHostAllocDefault));
-    std::memset(c->h_chunks, 0, n_chunks * 4);              // voxel.zig:34
-    std::memset(c->h_bricks, 0, brick_capacity * 2048);     // GL zero-initialised storage (SURVEY A.5)
     UVT_CUDA(c, cudaMalloc(&c->d_chunks, n_chunks * 4));
     UVT_CUDA(c, cudaMalloc(&c->d_chunks2, (size_t)(c->cd + 1) * (c->cd + 1) * (c->cd + 1) * 4));
     UVT_CUDA(c, cudaMalloc(&c->d_clear4, (size_t)(dim / 4) * (dim / 4) * 2));
+    return UVT_OK;
+}
+
+int uvt_world_alloc(uvt_ctx *c, uint32_t dim, uint32_t **chunks_host, uint32_t **bricks_host, size_t brick_capacity) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_REQUIRE(c, chunks_host && bricks_host, "NULL out pointer");
+    UVT_REQUIRE(c, dim >= 8 && dim % 8 == 0 && dim <= 4096, "dim must be a multiple of 8 in [8, 4096]");
+    UVT_REQUIRE(c, brick_capacity > 0, "brick_capacity must be > 0");
+    int rc = reset_world(c, dim);
+    if (rc != UVT_OK) return rc;
+    const size_t n_chunks = (size_t)c->cd * c->cd * c->cd;
+    UVT_CUDA(c, cudaHostAlloc(&c->h_chunks, n_chunks * 4, cudaHostAllocPortable));
+    UVT_CUDA(c, cudaHostAlloc(&c->h_bricks, brick_capacity * 2048, cudaHostAllocPortable));
+    std::memset(c->h_chunks, 0, n_chunks * 4);              // voxel.zig:34
+    std::memset(c->h_bricks, 0, brick_capacity * 2048);     // GL zero-initialised storage (SURVEY A.5)
     c->h_capacity = brick_capacity;
-    c->n_bricks = 0;
-    c->world_committed = false;
     *chunks_host = c->h_chunks;
     *bricks_host = c->h_bricks;
     return UVT_OK;
 }
 
+int uvt_world_use_staging(uvt_ctx *c, uint32_t dim, uint32_t *chunks_host, uint32_t *bricks_host, size_t brick_capacity) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_REQUIRE(c, bricks_host && brick_capacity > 0, "NULL brick pool");
+    if (dim == 0) {  // the caller's pool moved or grew: same world, new pool address
+        UVT_REQUIRE(c, c->staging_borrowed && c->h_chunks, "no caller-owned staging to update");
+        UVT_REQUIRE(c, brick_capacity >= c->h_capacity, "cannot shrink the brick pool (buffer.zig:51-52)");
+        UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->h_bricks = bricks_host;
+        c->h_capacity = brick_capacity;
+        return UVT_OK;
+    }
+    UVT_REQUIRE(c, chunks_host, "NULL chunk table");
+    UVT_REQUIRE(c, dim >= 8 && dim % 8 == 0 && dim <= 4096, "dim must be a multiple of 8 in [8, 4096]");
+    int rc = reset_world(c, dim);
+    if (rc != UVT_OK) return rc;
+    c->h_chunks = chunks_host;
+    c->h_bricks = bricks_host;
+    c->h_capacity = brick_capacity;
+    c->staging_borrowed = true;
+    return UVT_OK;
+}
+
 int uvt_world_grow(uvt_ctx *c, size_t new_capacity, uint32_t **bricks_host) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, c->h_bricks && bricks_host, "no world allocated");
+    UVT_REQUIRE(c, !c->staging_borrowed, "the staging belongs to the caller (uvt_world_use_staging): grow it there");
     UVT_REQUIRE(c, new_capacity >= c->h_capacity, "cannot shrink the brick pool (buffer.zig:51-52)");
     if (new_capacity == c->h_capacity) { *bricks_host = c->h_bricks; return UVT_OK; }
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));  // an upload may still be reading the old staging
     uint32_t *nb = nullptr;
-    UVT_CUDA(c, cudaHostAlloc(&nb, new_capacity * 2048, cudaHostAllocDefault));
+    UVT_CUDA(c, cudaHostAlloc(&nb, new_capacity * 2048, cudaHostAllocPortable));
     std::memcpy(nb, c->h_bricks, c->h_capacity * 2048);  // copyNamedBufferSubData (buffer.zig:57)
     std::memset((uint8_t *)nb + c->h_capacity * 2048, 0, (new_capacity - c->h_capacity) * 2048);
     cudaFreeHost(c->h_bricks);
@@ -767,6 +817,7 @@ int uvt_world_grow(uvt_ctx *c, size_t new_capacity, uint32_t **bricks_host) {
 
 int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, c->h_chunks && c->h_bricks, "no world allocated");
     UVT_REQUIRE(c, n_bricks <= c->h_capacity, "n_bricks exceeds the pool capacity");
     const size_t n_chunks = (size_t)c->cd * c->cd * c->cd;
@@ -822,6 +873,7 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
 // additionally refreshes the chunk distance field and gives newly adjacent empty chunks a virtual brick.
 int uvt_world_commit_region(uvt_ctx *c, size_t n_bricks, const uint32_t lo[3], const uint32_t hi[3]) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, c->h_chunks && c->h_bricks, "no world allocated");
     UVT_REQUIRE(c, lo && hi, "NULL box");
     UVT_REQUIRE(c, n_bricks <= c->h_capacity, "n_bricks exceeds the pool capacity");
@@ -974,6 +1026,7 @@ int uvt_world_commit_region(uvt_ctx *c, size_t n_bricks, const uint32_t lo[3], c
 // map_setVoxel (map.glsl:49-55): the write lands only where the chunk already holds a brick
 int uvt_world_set_voxel(uvt_ctx *c, uint32_t x, uint32_t y, uint32_t z, uint32_t voxel, int *written) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     if (written) *written = 0;
     UVT_REQUIRE(c, c->h_chunks && c->h_bricks && c->world_committed, "no world committed");
     if (x >= c->dim || y >= c->dim || z >= c->dim) return UVT_OK;  // map_getChunkFlags reads 0 outside the map
@@ -987,6 +1040,7 @@ int uvt_world_set_voxel(uvt_ctx *c, uint32_t x, uint32_t y, uint32_t z, uint32_t
 
 int uvt_world_layout_checksum(uvt_ctx *c, uint64_t out[4]) {
     if (!c || !out) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, c->world_committed, "no world committed");
     out[0] = out[1] = out[2] = out[3] = 0;
     if (!c->compact_ok) return UVT_OK;  // reference layout only: nothing derived
@@ -1013,6 +1067,7 @@ int uvt_world_layout_checksum(uvt_ctx *c, uint64_t out[4]) {
 // ---- atlas --------------------------------------------------------------------------------------
 int uvt_atlas_upload(uvt_ctx *c, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t w, uint32_t h, uint32_t d, const uint32_t *rgba) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, rgba, "rgba is NULL");
     UVT_REQUIRE(c, (uint64_t)ox + w <= 256 && (uint64_t)oy + h <= 256 && (uint64_t)oz + d <= 256, "sub-box leaves the 256^3 atlas");
     for (uint32_t z = 0; z < d; ++z)
@@ -1035,6 +1090,7 @@ int uvt_set_camera(uvt_ctx *c, const uvt_camera *cam) { return uvt_set_cameras(c
 
 int uvt_set_cameras(uvt_ctx *c, const uvt_camera *cams, int n) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, cams && n >= 1, "need at least one camera");
     c->cams.assign(cams, cams + n);
     derive_cam(cams[0], c->cam0);
@@ -1066,6 +1122,7 @@ int uvt_set_cameras(uvt_ctx *c, const uvt_camera *cams, int n) {
 // ---- G-buffer -----------------------------------------------------------------------------------
 int uvt_resize(uvt_ctx *c, uint32_t width, uint32_t height) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, width >= 1 && height >= 1 && width <= 32768 && height <= 32768, "G-buffer size out of range");
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->W = width;
@@ -1075,6 +1132,7 @@ int uvt_resize(uvt_ctx *c, uint32_t width, uint32_t height) {
 
 int uvt_set_partition(uvt_ctx *c, uint32_t band_rows, uint32_t n_parts, uint32_t part) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, n_parts >= 1 && part < n_parts, "part must be < n_parts");
     UVT_REQUIRE(c, band_rows >= 8 && band_rows % 8 == 0 && band_rows % kTileH == 0, "band_rows must be a positive multiple of 8 (and of the CTA tile height)");
     UVT_REQUIRE(c, n_parts == 1 || band_rows % kPoolTile == 0, "with more than one part band_rows must be a multiple of 16 (the pooled CTA tile)");
@@ -1088,6 +1146,7 @@ int uvt_set_partition(uvt_ctx *c, uint32_t band_rows, uint32_t n_parts, uint32_t
 
 int uvt_local_rows(uvt_ctx *c, uint32_t *rows) {
     if (!c || !rows) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     *rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
     return UVT_OK;
 }
@@ -1095,6 +1154,7 @@ int uvt_local_rows(uvt_ctx *c, uint32_t *rows) {
 // ---- passes -------------------------------------------------------------------------------------
 int uvt_dispatch_primary(uvt_ctx *c) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     int rc = pre_dispatch(c);
     if (rc != UVT_OK) return rc;
     PassTimer t(c, 0);
@@ -1103,6 +1163,7 @@ int uvt_dispatch_primary(uvt_ctx *c) {
 
 int uvt_dispatch_secondary(uvt_ctx *c) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     int rc = pre_dispatch(c);
     if (rc != UVT_OK) return rc;
     PassTimer t(c, 1);
@@ -1111,6 +1172,7 @@ int uvt_dispatch_secondary(uvt_ctx *c) {
 
 int uvt_shade(uvt_ctx *c) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, c->W && c->H, "no G-buffer (uvt_resize first)");
     const uint32_t rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
     const dim3 grid((c->W + 63) / 64, (rows + 3) / 4, c->layers);
@@ -1121,6 +1183,7 @@ int uvt_shade(uvt_ctx *c) {
 
 int uvt_dispatch_frame(uvt_ctx *c) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     int rc = pre_dispatch(c);
     if (rc != UVT_OK) return rc;
     const ViewDev v = make_view(c, c->params.primary_max_steps);
@@ -1157,6 +1220,7 @@ int uvt_dispatch_frame(uvt_ctx *c) {
 
 int uvt_pick(uvt_ctx *c, uvt_hit *out) {
     if (!c || !out) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, c->have_camera, "no camera (uvt_set_camera first)");
     int rc = ensure_ready(c);
     if (rc != UVT_OK) return rc;
@@ -1172,6 +1236,7 @@ int uvt_pick(uvt_ctx *c, uvt_hit *out) {
 
 int uvt_sync(uvt_ctx *c) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     return UVT_OK;
 }
@@ -1192,6 +1257,7 @@ static int buffer_info(uvt_ctx *c, uvt_buffer_kind kind, void **ptr, size_t *byt
 
 size_t uvt_buffer_bytes(uvt_ctx *c, uvt_buffer_kind kind) {
     if (!c) return 0;
+    UVT_ENTER(c);
     void *p = nullptr;
     size_t bpp = 0;
     if (buffer_info(c, kind, &p, &bpp) != UVT_OK) return 0;
@@ -1200,6 +1266,7 @@ size_t uvt_buffer_bytes(uvt_ctx *c, uvt_buffer_kind kind) {
 
 int uvt_readback(uvt_ctx *c, uvt_buffer_kind kind, void *dst, size_t bytes) {
     if (!c || !dst) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     void *p = nullptr;
     size_t bpp = 0;
     int rc = buffer_info(c, kind, &p, &bpp);
@@ -1212,6 +1279,7 @@ int uvt_readback(uvt_ctx *c, uvt_buffer_kind kind, void *dst, size_t bytes) {
 
 int uvt_readback_async(uvt_ctx *c, uvt_buffer_kind kind, void *dst, size_t bytes) {
     if (!c || !dst) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     void *p = nullptr;
     size_t bpp = 0;
     int rc = buffer_info(c, kind, &p, &bpp);
@@ -1241,6 +1309,7 @@ int uvt_readback_async(uvt_ctx *c, uvt_buffer_kind kind, void *dst, size_t bytes
 
 int uvt_readback_wait(uvt_ctx *c) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     for (int s = 0; s < 2; ++s)
         if (c->snap_busy[s]) {
             UVT_CUDA(c, cudaEventSynchronize(c->snap_done[s]));
@@ -1251,12 +1320,14 @@ int uvt_readback_wait(uvt_ctx *c) {
 
 int uvt_device_ptr(uvt_ctx *c, uvt_buffer_kind kind, void **dptr) {
     if (!c || !dptr) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     size_t bpp;
     return buffer_info(c, kind, dptr, &bpp);
 }
 
 int uvt_bind_frame_target(uvt_ctx *c, void *dptr, uint32_t row_offset_rows, uint32_t global_rows) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     (void)row_offset_rows;
     c->frame_target = (uint32_t *)dptr;
     c->frame_target_global_rows = global_rows != 0;
@@ -1265,6 +1336,7 @@ int uvt_bind_frame_target(uvt_ctx *c, void *dptr, uint32_t row_offset_rows, uint
 
 int uvt_shared_frame_create(uvt_ctx *c, void **dptr, unsigned char handle_out[64]) {
     if (!c || !dptr || !handle_out) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, c->W && c->H, "no G-buffer (uvt_resize first)");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1281,6 +1353,7 @@ int uvt_shared_frame_create(uvt_ctx *c, void **dptr, unsigned char handle_out[64
 
 int uvt_shared_frame_open(uvt_ctx *c, const unsigned char handle[64], void **dptr) {
     if (!c || !dptr || !handle) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle, 64);
     UVT_CUDA(c, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
@@ -1289,6 +1362,7 @@ int uvt_shared_frame_open(uvt_ctx *c, const unsigned char handle[64], void **dpt
 
 int uvt_shared_frame_close(uvt_ctx *c, void *dptr) {
     if (!c || !dptr) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->frame_target == dptr) c->frame_target = nullptr;
     UVT_CUDA(c, cudaIpcCloseMemHandle(dptr));
@@ -1297,6 +1371,7 @@ int uvt_shared_frame_close(uvt_ctx *c, void *dptr) {
 
 int uvt_read_device(uvt_ctx *c, const void *dptr, void *dst, size_t bytes) {
     if (!c || !dptr || !dst) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_CUDA(c, cudaMemcpyAsync(dst, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     return UVT_OK;
@@ -1304,18 +1379,21 @@ int uvt_read_device(uvt_ctx *c, const void *dptr, void *dst, size_t bytes) {
 
 int uvt_alloc_pinned(uvt_ctx *c, size_t bytes, void **out) {
     if (!c || !out) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_CUDA(c, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
     return UVT_OK;
 }
 
 int uvt_free_pinned(uvt_ctx *c, void *p) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_CUDA(c, cudaFreeHost(p));
     return UVT_OK;
 }
 
 int uvt_count_pass(uvt_ctx *c, int which, uvt_counters *out) {
     if (!c || !out) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, which >= 0 && which <= 3, "which must be 0/1 (reference counters) or 2/3 (fast-path fetch statistics) for primary/secondary");
     int rc = pre_dispatch(c);
     if (rc != UVT_OK) return rc;
@@ -1332,12 +1410,14 @@ int uvt_count_pass(uvt_ctx *c, int which, uvt_counters *out) {
 
 int uvt_enable_timing(uvt_ctx *c, int on) {
     if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     c->timing = on != 0;
     return UVT_OK;
 }
 
 int uvt_last_pass_ms(uvt_ctx *c, int which, float *ms) {
     if (!c || !ms) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, which >= 0 && which < 4, "which must be 0..3");
     UVT_REQUIRE(c, c->ev_valid[which], "pass has not run with timing enabled");
     UVT_CUDA(c, cudaEventSynchronize(c->ev[which][1]));
@@ -1349,6 +1429,7 @@ uint64_t uvt_launch_count(uvt_ctx *c) { return c ? c->launches : 0; }
 
 int uvt_deinterleave(uvt_ctx *c, const void *gathered, void *frame, uint32_t rows_per_part) {
     if (!c || !gathered || !frame) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     const dim3 grid((c->W + 255) / 256, c->H, 1);
     deinterleave_kernel<<<grid, 256, 0, c->stream>>>((const uint32_t *)gathered, (uint32_t *)frame, c->W, c->H, c->band_rows, c->n_parts, rows_per_part);
     return check_launch(c, "deinterleave_kernel");
@@ -1356,6 +1437,7 @@ int uvt_deinterleave(uvt_ctx *c, const void *gathered, void *frame, uint32_t row
 
 int uvt_measure_l2_read_gbps(uvt_ctx *c, size_t bytes, int repeats, float *gbps) {
     if (!c || !gbps) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, bytes >= 4096 && bytes % 16 == 0 && repeats >= 1, "bytes must be a multiple of 16, repeats >= 1");
     uint4 *buf = nullptr;
     UVT_CUDA(c, cudaMalloc(&buf, bytes));
@@ -1381,6 +1463,7 @@ int uvt_measure_l2_read_gbps(uvt_ctx *c, size_t bytes, int repeats, float *gbps)
 
 int uvt_measure_hbm_copy_gbps(uvt_ctx *c, size_t bytes, int repeats, float *gbps) {
     if (!c || !gbps) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
     UVT_REQUIRE(c, bytes >= 4096 && bytes % 16 == 0 && repeats >= 1, "bytes must be a multiple of 16, repeats >= 1");
     uint4 *src = nullptr, *dst = nullptr;
     UVT_CUDA(c, cudaMalloc(&src, bytes));

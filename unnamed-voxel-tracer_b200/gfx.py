@@ -37,6 +37,17 @@ def _check(ctx_handle, rc):
     return rc
 
 
+def _check_owner(owner, rc):
+    """owner: a Context or a Group (or None)."""
+    if rc != N.UVT_OK:
+        if owner is not None and getattr(owner, "is_group", False):
+            msg = N.load().uvt_group_last_error(owner.handle)
+        else:
+            msg = N.load().uvt_last_error(owner.handle if owner is not None else None)
+        raise UvtError(rc, msg.decode() if msg else "")
+    return rc
+
+
 class Context:
     """gfx.init (graphics.zig:60-75): one CUDA device + one in-order stream."""
 
@@ -261,6 +272,78 @@ class Context:
 def init(device=0, **kw):
     """gfx.init(window) (graphics.zig:60): returns the context every wrapper below hangs off."""
     return Context(device, **kw)
+
+
+
+class Group:
+    """Several GPUs behind one handle in ONE process (uvt_group, include/uvt.h): world and atlas replicated, the frame
+    cut into interleaved 32-row bands, every member storing its bands into member 0's frame over NVLink."""
+
+    is_group = True
+
+    def __init__(self, devices, *, map_dim=512, primary_max_steps=192, shadow_max_steps=48, hit_buffer=False, entities=True):
+        L = N.load()
+        p = N.Params()
+        L.uvt_default_params(ctypes.byref(p))
+        p.map_dim = map_dim
+        p.primary_max_steps = primary_max_steps
+        p.shadow_max_steps = shadow_max_steps
+        p.flags = (N.UVT_FLAG_HIT_BUFFER if hit_buffer else 0) | (N.UVT_FLAG_ENTITIES if entities else 0)
+        devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        h = ctypes.c_void_p()
+        rc = L.uvt_group_create(ctypes.byref(p), devs, len(devices), ctypes.byref(h))
+        if rc != N.UVT_OK:
+            msg = L.uvt_group_last_error(None)
+            raise UvtError(rc, msg.decode() if msg else "")
+        self.handle, self.L, self.devices = h, L, list(devices)
+        self.W = self.H = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.L.uvt_group_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def check(self, rc):
+        return _check_owner(self, rc)
+
+    @property
+    def size(self):
+        return int(self.L.uvt_group_size(self.handle))
+
+    def member_handle(self, i):
+        return ctypes.c_void_p(self.L.uvt_group_member(self.handle, i))
+
+    def set_camera(self, cam):
+        buf = np.ascontiguousarray(cam)
+        assert buf.nbytes == 96
+        self.check(self.L.uvt_group_set_camera(self.handle, buf.ctypes.data))
+
+    def resize(self, w, h):
+        self.check(self.L.uvt_group_resize(self.handle, w, h))
+        self.W, self.H = w, h
+
+    def dispatch_frame(self):
+        self.check(self.L.uvt_group_dispatch_frame(self.handle))
+
+    def sync(self):
+        self.check(self.L.uvt_group_sync(self.handle))
+
+    def readback_frame(self, out=None):
+        if out is None:
+            out = np.empty((self.H, self.W), dtype=np.uint32)
+        self.check(self.L.uvt_group_readback_frame(self.handle, out.ctypes.data, out.nbytes))
+        return out
+
+    def count_pass(self, which):
+        c = N.Counters()
+        self.check(self.L.uvt_group_count_pass(self.handle, {"primary": 0, "secondary": 1}[which], ctypes.byref(c)))
+        return c.as_dict()
 
 
 class ComputePipeline:

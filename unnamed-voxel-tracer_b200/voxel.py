@@ -9,7 +9,7 @@ import ctypes
 import numpy as np
 
 from . import _native as N
-from .gfx import UvtError, _check
+from .gfx import UvtError, _check, _check_owner
 
 TY_MASK = 0x0FFFFFFF
 SOLID = 0x10000000
@@ -31,9 +31,11 @@ class VoxelBrickmap:
         self.dim = dim
         self._L = N.load()
         h = ctypes.c_void_p()
-        rc = self._L.uvt_brickmap_create(ctx.handle if ctx else None, dim, ctypes.byref(h))
-        if rc != N.UVT_OK:
-            _check(ctx.handle if ctx else None, rc)
+        if ctx is not None and getattr(ctx, "is_group", False):
+            rc = self._L.uvt_brickmap_create_group(ctx.handle, dim, ctypes.byref(h))
+        else:
+            rc = self._L.uvt_brickmap_create(ctx.handle if ctx else None, dim, ctypes.byref(h))
+        _check_owner(ctx, rc)
         self.handle = h
 
     @classmethod
@@ -106,7 +108,7 @@ class VoxelBrickmap:
             raise UvtError(N.UVT_ERR_INVALID, "voxelData/mapData are bindings 9/10 (map.glsl:11-17)")
         if not self.ctx:
             raise UvtError(N.UVT_ERR_INVALID, "brickmap has no ctx to bind to")
-        _check(self.ctx.handle, self._L.uvt_brickmap_bind(self.handle))
+        _check_owner(self.ctx, self._L.uvt_brickmap_bind(self.handle))
 
     def deinit(self):
         if self.handle:
@@ -119,7 +121,10 @@ class VoxelModelAtlas:
         self.ctx = ctx
         self._L = N.load()
         h = ctypes.c_void_p()
-        rc = self._L.uvt_atlas_create(ctx.handle if ctx else None, ctypes.byref(h))
+        if ctx is not None and getattr(ctx, "is_group", False):
+            rc = self._L.uvt_atlas_create_group(ctx.handle, ctypes.byref(h))
+        else:
+            rc = self._L.uvt_atlas_create(ctx.handle if ctx else None, ctypes.byref(h))
         if rc != N.UVT_OK:
             raise UvtError(rc, "atlas create failed")
         self.handle = h
