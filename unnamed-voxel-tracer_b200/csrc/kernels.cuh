@@ -494,11 +494,27 @@ __global__ void repack_bricks_kernel(const uint32_t *__restrict__ bricks, uint8_
 constexpr int kFieldCap = 32;
 constexpr uint32_t kNoChunk = 0xFFFFFFFFu;  // brick_chunk[] of a brick slot no chunk uses
 
-__global__ void field_pass_x_kernel(const uint32_t *__restrict__ chunks, uint8_t *__restrict__ out, int cd) {
-    const size_t n = (size_t)cd * cd * cd;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int x = (int)(i % cd);
+// The commit kernels below run over a box of chunks (the whole map for a full commit, the neighbourhood of an edit for
+// an incremental one): thread t -> chunk (x, y, z) of the box, i = its linear index in the map.
+struct ChunkBox {
+    int ox, oy, oz, ex, ey, ez;
+    __host__ __device__ size_t count() const { return (size_t)ex * ey * ez; }
+};
+
+__device__ __forceinline__ bool box_chunk(const ChunkBox &b, int cd, int &x, int &y, int &z, size_t &i) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= b.count()) return false;
+    x = b.ox + (int)(t % b.ex);
+    y = b.oy + (int)((t / b.ex) % b.ey);
+    z = b.oz + (int)(t / ((size_t)b.ex * b.ey));
+    i = (size_t)x + (size_t)cd * ((size_t)y + (size_t)z * cd);
+    return true;
+}
+
+__global__ void field_pass_x_kernel(const uint32_t *__restrict__ chunks, uint8_t *__restrict__ out, int cd, ChunkBox box) {
+    int x, y, z;
+    size_t i;
+    if (!box_chunk(box, cd, x, y, z, i)) return;
     int best = kFieldCap;
     if (chunks[i] != 0) best = 0;
     else {
@@ -511,12 +527,13 @@ __global__ void field_pass_x_kernel(const uint32_t *__restrict__ chunks, uint8_t
     out[i] = (uint8_t)best;
 }
 
-// axis stride `stride`, coordinate along the axis = (i / stride) % cd
-__global__ void field_pass_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int cd, size_t stride) {
-    const size_t n = (size_t)cd * cd * cd;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int a = (int)((i / stride) % cd);
+// axis 1 = y (stride cd), axis 2 = z (stride cd^2); a value depends on inputs at most kFieldCap - 1 chunks away along the axis
+__global__ void field_pass_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int cd, int axis, ChunkBox box) {
+    int x, y, z;
+    size_t i;
+    if (!box_chunk(box, cd, x, y, z, i)) return;
+    const int a = axis == 1 ? y : z;
+    const size_t stride = axis == 1 ? (size_t)cd : (size_t)cd * cd;
     int best = in[i];
     for (int k = 1; k < best; ++k) {
         const int lo = (a - k < 0) ? 0 : (int)in[i - (size_t)k * stride];
@@ -755,13 +772,12 @@ __global__ void __launch_bounds__(64) repack_list_kernel(const uint32_t *__restr
 
 // empty chunks that newly touch a non-empty chunk and hold no virtual brick yet
 __global__ void count_new_virtual_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ dist, const uint32_t *__restrict__ chunks2,
-                                         int cd, uint32_t v_base, unsigned int *counter) {
-    const size_t n = (size_t)cd * cd * cd;
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                         int cd, uint32_t v_base, unsigned int *counter, ChunkBox box) {
+    int x, y, z;
+    size_t j;
     bool v = false;
-    if (j < n && chunks[j] == 0 && dist[j] == 1) {
+    if (box_chunk(box, cd, x, y, z, j) && chunks[j] == 0 && dist[j] == 1) {
         const int cd1 = cd + 1;
-        const int x = (int)(j % cd), y = (int)((j / cd) % cd), z = (int)(j / ((size_t)cd * cd));
         const uint32_t old = chunks2[(size_t)x + (size_t)cd1 * ((size_t)y + (size_t)z * cd1)];
         v = (int)old < 0 || old < v_base;
     }
@@ -774,12 +790,11 @@ __global__ void count_new_virtual_kernel(const uint32_t *__restrict__ chunks, co
 __global__ void update_chunks2_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ dist, uint32_t *__restrict__ chunks2,
                                       uint32_t *__restrict__ brick_chunk, uint8_t *__restrict__ bricks8, uint8_t *__restrict__ rowmask, int cd,
                                       uint32_t v_base, unsigned int *n_virtual, uint32_t *__restrict__ changed_list, uint32_t changed_cap,
-                                      unsigned int *changed_count) {
-    const size_t n = (size_t)cd * cd * cd;
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+                                      unsigned int *changed_count, ChunkBox box) {
+    int x, y, z;
+    size_t j;
+    if (!box_chunk(box, cd, x, y, z, j)) return;
     const int cd1 = cd + 1;
-    const int x = (int)(j % cd), y = (int)((j / cd) % cd), z = (int)(j / ((size_t)cd * cd));
     const size_t i = (size_t)x + (size_t)cd1 * ((size_t)y + (size_t)z * cd1);
     const uint32_t old = chunks2[i];
     const uint32_t c = chunks[j];

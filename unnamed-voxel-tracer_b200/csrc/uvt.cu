@@ -56,6 +56,8 @@ struct uvt_ctx {
     uint8_t *d_rowmask = nullptr;       // [d_brick8_capacity][64] x-occupancy bits of every brick row
     uint32_t *d_brick_chunk = nullptr;  // [d_brick8_capacity] brick slot -> linear chunk index (kNoChunk: unused)
     unsigned int *d_tops32 = nullptr;   // [dim^2] column tops (block y + 1)
+    uint8_t *d_field = nullptr;         // [(dim/8)^3] chunk distance field of the committed world
+    uint8_t *d_field_tmp[2] = {nullptr, nullptr};  // separable-pass scratch, same size
     uint32_t *d_scratch = nullptr;      // staging of uvt_world_commit_region (kScratchWords)
     bool incremental_ok = false;        // the last full commit left everything uvt_world_commit_region needs
     int32_t y_clear = 0;            // max occupied block y + 1 (every block at or above is empty)
@@ -455,8 +457,7 @@ int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
     const size_t n_chunks = (size_t)cd * cd * cd;
     const size_t n2 = (size_t)(cd + 1) * (cd + 1) * (cd + 1);
     c->incremental_ok = false;
-    uint8_t *f0 = nullptr, *f1 = nullptr;
-    auto cleanup = [&]() { cudaFree(f0); cudaFree(f1); };
+    auto cleanup = [&]() {};
 #define UVT_CUDA_C(expr)                                                                                      \
     do {                                                                                                      \
         cudaError_t e_ = (expr);                                                                              \
@@ -468,12 +469,17 @@ int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
     } while (0)
     if (!c->d_scratch) UVT_CUDA_C(cudaMalloc(&c->d_scratch, kScratchWords * 4));
     unsigned int *d_counter = reinterpret_cast<unsigned int *>(c->d_scratch + kScrFlags);
-    UVT_CUDA_C(cudaMalloc(&f0, n_chunks));
-    UVT_CUDA_C(cudaMalloc(&f1, n_chunks));
+    if (!c->d_field) {
+        UVT_CUDA_C(cudaMalloc(&c->d_field, n_chunks));
+        UVT_CUDA_C(cudaMalloc(&c->d_field_tmp[0], n_chunks));
+        UVT_CUDA_C(cudaMalloc(&c->d_field_tmp[1], n_chunks));
+    }
+    uint8_t *f0 = c->d_field;
     const unsigned cblocks = (unsigned)((n_chunks + 255) / 256);
-    field_pass_x_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, cd);
-    field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(f0, f1, cd, (size_t)cd);
-    field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(f1, f0, cd, (size_t)cd * cd);
+    const ChunkBox whole = {0, 0, 0, cd, cd, cd};
+    field_pass_x_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, c->d_field_tmp[0], cd, whole);
+    field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_field_tmp[0], c->d_field_tmp[1], cd, 1, whole);
+    field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_field_tmp[1], f0, cd, 2, whole);
     UVT_CUDA_C(cudaMemsetAsync(d_counter, 0, 4, c->stream));
     count_virtual_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, n_chunks, d_counter);
     unsigned int n_virtual = 0;
@@ -634,6 +640,7 @@ void uvt_destroy(uvt_ctx *c) {
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
     cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
     cudaFree(c->d_rowmask); cudaFree(c->d_brick_chunk); cudaFree(c->d_tops32); cudaFree(c->d_scratch);
+    cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
     cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame);
     for (int i = 0; i < 4; ++i)
@@ -732,6 +739,8 @@ static int reset_world(uvt_ctx *c, uint32_t dim) {
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
     cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32);
+    cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]);
+    c->d_field = c->d_field_tmp[0] = c->d_field_tmp[1] = nullptr;
     c->d_dense = nullptr;
     c->d_tops32 = nullptr;
     c->incremental_ok = false;
@@ -947,37 +956,40 @@ int uvt_world_commit_region(uvt_ctx *c, size_t n_bricks, const uint32_t lo[3], c
 
     unsigned int n_changed = 0;
     if (table_changed) {
-        // distance field -> new virtual bricks -> chunks2
-        const size_t n_chunks = (size_t)cd * cd * cd;
-        const unsigned cblocks = (unsigned)((n_chunks + 255) / 256);
-        uint8_t *f0 = nullptr, *f1 = nullptr;
-        if (cudaMalloc(&f0, n_chunks) != cudaSuccess || cudaMalloc(&f1, n_chunks) != cudaSuccess) {
-            cudaFree(f0); cudaFree(f1);
-            (void)cudaGetLastError();
-            return set_error(c, UVT_ERR_OOM, "no memory for the chunk distance field");
-        }
-        field_pass_x_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, cd);
-        field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(f0, f1, cd, (size_t)cd);
-        field_pass_kernel<<<cblocks, 256, 0, c->stream>>>(f1, f0, cd, (size_t)cd * cd);
-        count_new_virtual_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, c->d_chunks2, cd, (uint32_t)c->v_base, d_flags + 1);
+        // distance field -> new virtual bricks -> chunks2.  A distance depends on the chunks within kFieldCap - 1 of it on
+        // every axis, so only the box grown by R = kFieldCap can change; the separable passes need their inputs one R further
+        // along the axes still to come.
+        const int R = kFieldCap;
+        const int ext[3] = {bx, by, bz};
+        auto grown = [&](int rx, int ry, int rz) {
+            const int r[3] = {rx, ry, rz};
+            int lo3[3], hi3[3];
+            for (int a = 0; a < 3; ++a) {
+                lo3[a] = std::max(o[a] - r[a], 0);
+                hi3[a] = std::min(o[a] + ext[a] - 1 + r[a], cd - 1);
+            }
+            return ChunkBox{lo3[0], lo3[1], lo3[2], hi3[0] - lo3[0] + 1, hi3[1] - lo3[1] + 1, hi3[2] - lo3[2] + 1};
+        };
+        auto blocks_of = [](const ChunkBox &b) { return (unsigned)((b.count() + 255) / 256); };
+        const ChunkBox bx_ = grown(R, 2 * R, 2 * R), by_ = grown(R, R, 2 * R), bz_ = grown(R, R, R);
+        field_pass_x_kernel<<<blocks_of(bx_), 256, 0, c->stream>>>(c->d_chunks, c->d_field_tmp[0], cd, bx_);
+        field_pass_kernel<<<blocks_of(by_), 256, 0, c->stream>>>(c->d_field_tmp[0], c->d_field_tmp[1], cd, 1, by_);
+        field_pass_kernel<<<blocks_of(bz_), 256, 0, c->stream>>>(c->d_field_tmp[1], c->d_field, cd, 2, bz_);
+        count_new_virtual_kernel<<<blocks_of(bz_), 256, 0, c->stream>>>(c->d_chunks, c->d_field, c->d_chunks2, cd, (uint32_t)c->v_base, d_flags + 1, bz_);
         c->launches += 4;
         unsigned int n_new = 0;
         cudaError_t e = cudaMemcpyAsync(&n_new, d_flags + 1, 4, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess || c->v_base + c->n_virtual + n_new > c->d_brick8_capacity) {
-            cudaFree(f0); cudaFree(f1);
-            if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "distance field: %s", cudaGetErrorString(e));
-            return uvt_world_commit(c, n_bricks);  // out of virtual-brick slots: rebuild with fresh capacity
-        }
+        if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "distance field: %s", cudaGetErrorString(e));
+        if (c->v_base + c->n_virtual + n_new > c->d_brick8_capacity) return uvt_world_commit(c, n_bricks);  // out of virtual-brick slots: rebuild
         unsigned int nv = (unsigned int)c->n_virtual;
         cudaMemcpyAsync(d_flags + 2, &nv, 4, cudaMemcpyHostToDevice, c->stream);
-        update_chunks2_kernel<<<cblocks, 256, 0, c->stream>>>(c->d_chunks, f0, c->d_chunks2, c->d_brick_chunk, c->d_bricks8, c->d_rowmask, cd,
-                                                              (uint32_t)c->v_base, d_flags + 2, d_changed, (uint32_t)kMaxChanged, d_flags + 3);
+        update_chunks2_kernel<<<blocks_of(bz_), 256, 0, c->stream>>>(c->d_chunks, c->d_field, c->d_chunks2, c->d_brick_chunk, c->d_bricks8, c->d_rowmask, cd,
+                                                                    (uint32_t)c->v_base, d_flags + 2, d_changed, (uint32_t)kMaxChanged, d_flags + 3, bz_);
         c->launches++;
         unsigned int out[2] = {0, 0};
         e = cudaMemcpyAsync(out, d_flags + 2, 8, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        cudaFree(f0); cudaFree(f1);
         if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "chunks2 update: %s", cudaGetErrorString(e));
         c->n_virtual = out[0];
         c->n_total_bricks = c->v_base + c->n_virtual;
