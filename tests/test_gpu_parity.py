@@ -711,3 +711,52 @@ def test_group_across_two_gpus(uvt, oracle, scene_factory):
         ctx.dispatch_frame()
         grp.dispatch_frame()
         assert np.array_equal(grp.readback_frame(), ctx.readback("frame"))
+
+
+def test_incremental_commit_random_edit_sequences(uvt, oracle, scene_factory, tmp_path):
+    """Forty random edit batches on a 64^3 world (single blocks, boxes, columns; set and clear; map faces and corners),
+    one bind() each: after every batch the derived layout equals a fresh full commit's, and every fifth batch the
+    pixels do too."""
+    V = uvt.voxel.Voxel
+    rng = np.random.default_rng(2024)
+    dim = 64
+    mats = [V(11, True), V(13, True), V(21, True), V(8, False), 0, 0]
+    with uvt.Context(0, hit_buffer=True) as ctx:
+        sc = scene_factory(dim, "procgen", ctx=ctx)
+        ctx.resize(96, 64)
+        cam = oracle.make_camera((32.0, 30.0, 4.0), pitch_yaw_matrix(uvt, 0.45, 0.0))
+        for batch in range(40):
+            kind = int(rng.integers(0, 4))
+            if kind == 0:      # scattered single blocks, anywhere (faces and corners included)
+                for _ in range(int(rng.integers(1, 6))):
+                    x, y, z = (int(v) for v in rng.choice([0, 1, 7, 8, 31, 32, 55, 56, 62, 63], 3))
+                    sc.bm.set(x, y, z, mats[int(rng.integers(0, len(mats)))])
+            elif kind == 1:    # a small box
+                lo = rng.integers(0, dim - 6, 3)
+                ext = rng.integers(1, 6, 3)
+                m = mats[int(rng.integers(0, len(mats)))]
+                for x in range(lo[0], lo[0] + ext[0]):
+                    for y in range(lo[1], lo[1] + ext[1]):
+                        for z in range(lo[2], lo[2] + ext[2]):
+                            sc.bm.set(int(x), int(y), int(z), m)
+            elif kind == 2:    # a column through every chunk row
+                x, z = (int(v) for v in rng.integers(0, dim, 2))
+                m = mats[int(rng.integers(0, len(mats)))]
+                for y in range(int(rng.integers(0, 8)), dim, int(rng.integers(1, 4))):
+                    sc.bm.set(x, y, z, m)
+            else:              # dig around the terrain surface
+                for _ in range(20):
+                    x, z = (int(v) for v in rng.integers(0, dim, 2))
+                    sc.bm.set(x, int(rng.integers(0, 20)), z, 0)
+            sc.bm.bind(9)
+            ctx2, _ = _fresh_full_commit(uvt, sc, tmp_path)
+            try:
+                assert ctx.world_layout_checksum()[:4] == ctx2.world_layout_checksum()[:4], (batch, kind)
+                if batch % 5 == 4:
+                    ctx2.resize(96, 64)
+                    a = gpu_render(ctx, cam)
+                    _same_render(a, gpu_render(ctx2, cam))
+                    world = oracle.World(dim, sc.bm.chunks().copy(), sc.bm.bricks().copy(), sc.oracle_world.atlas)
+                    assert_primary_parity(a, oracle.render(world, cam, 96, 64))
+            finally:
+                ctx2.close()

@@ -625,6 +625,18 @@ __global__ void quad_clear_kernel(const unsigned int *__restrict__ tops32, uint1
     clear4[i] = (uint16_t)m;
 }
 
+// clear64[Q] = max of clear4 over the 16x16 groups of the 64x64-block column group Q (the last one may be partial)
+__global__ void coarse_clear_kernel(const uint16_t *__restrict__ clear4, uint16_t *__restrict__ clear64, int dim) {
+    const int qdim = dim >> 2, cdim = (dim + 63) >> 6;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cdim * cdim) return;
+    const int cx = i % cdim, cz = i / cdim;
+    unsigned int m = 0;
+    for (int z = 16 * cz; z < min(16 * cz + 16, qdim); ++z)
+        for (int x = 16 * cx; x < min(16 * cx + 16, qdim); ++x) m = max(m, (unsigned int)clear4[x + qdim * z]);
+    clear64[i] = (uint16_t)m;
+}
+
 // Block-level clearance.  One CTA per brick, one thread per block.  The occupancy of the 5x5x5 chunk
 // neighbourhood is staged in shared memory as 40x40 rows of 40 x-bits (out-of-map = occupied); each
 // empty block searches growing Chebyshev shells for the nearest occupied block, D capped at 16, and

@@ -108,7 +108,7 @@ __device__ __forceinline__ void pool_advance(const WorldCompact &w, const uint32
 
     // sealed-ray test (c) at the phase boundary, all candidate rays at once (see trace.cuh)
     if (COUNT != 1 && climbs && limit < kDead && (big || trip == 0) &&
-        sky_sealed(w.clear4, w.dim, w.y_clear, ((float)gx + wx) * 0.125f, ((float)gy + wy) * 0.125f, ((float)gz + wz) * 0.125f, dx, dy, dz, max_steps - trip)) {
+        sky_sealed(w.clear4, w.clear64, w.dim, w.y_clear, ((float)gx + wx) * 0.125f, ((float)gy + wy) * 0.125f, ((float)gz + wz) * 0.125f, dx, dy, dz, max_steps - trip)) {
         out.trips = (uint32_t)max_steps;  // iteration-cap miss (map.glsl:167)
         limit = kDead;
     }

@@ -86,6 +86,7 @@ struct WorldCompact {
     int32_t dim;                            // MAP_DIMENSION in blocks
     const uint8_t *__restrict__ dense;      // [dim^3] one byte per block, x + dim*(z + dim*y): the brick bytes (far-empty chunks:
                                             // kMatLimit + min(n_free, 30)) without the chunk indirection; nullptr when not built
+    const uint16_t *__restrict__ clear64;   // [ceil(dim/64)^2] maximum of clear4 over 64x64-block column groups (coarse sky_sealed walk)
     const uint16_t *__restrict__ clear4;    // [(dim/4)^2] per 4x4-block column group, grown by one block on every side:
                                             // every block with y >= clear4 there is empty (sky_sealed)
 
@@ -226,29 +227,38 @@ __device__ __forceinline__ void trace_map(const World &w, float ox, float oy, fl
 // a 2-D DDA until the line has covered more blocks (L1) than the remaining trips can cross, or has risen
 // above the whole world.  It decides only WHETHER lookups can be skipped, never a hit, so it needs no
 // bit-exact arithmetic.  (px, py, pz) in blocks, d = the ray direction with zero components patched.
-__device__ __noinline__ bool sky_sealed(const uint16_t *__restrict__ clear4, int dim, int y_clear, float px, float py, float pz,
-                                        float dx, float dy, float dz, int trips_left) {
-    const float inv_dx = 1.0f / dx, inv_dz = 1.0f / dz;
-    int qx = (int)(px * 0.25f), qz = (int)(pz * 0.25f);
-    const int qdim = dim >> 2;
+// CELL = blocks per column group: 4 (clear4) or 64 (clear64, the maximum of clear4 over 16x16 groups).
+template <int CELL>
+__device__ __forceinline__ bool sky_walk(const uint16_t *__restrict__ tops, int qdim, float y_all, float px, float py, float pz,
+                                         float dx, float dy, float dz, float inv_dx, float inv_dz, float t_stop) {
+    int qx = (int)(px * (1.0f / CELL)), qz = (int)(pz * (1.0f / CELL));
     const int sx = dx > 0.0f ? 1 : -1, sz = dz > 0.0f ? 1 : -1;
-    float tmx = ((float)((qx + (dx > 0.0f ? 1 : 0)) * 4) - px) * inv_dx;  // line parameter at the next x / z group boundary
-    float tmz = ((float)((qz + (dz > 0.0f ? 1 : 0)) * 4) - pz) * inv_dz;
-    const float tdx = 4.0f * fabsf(inv_dx), tdz = 4.0f * fabsf(inv_dz);
-    // each trip crosses one block boundary, so after n trips the line has covered about n blocks in L1
-    const float t_stop = (float)(trips_left + 4) / (fabsf(dx) + fabsf(dy) + fabsf(dz));
-    const float y_all = (float)y_clear + 2.0f;
+    float tmx = ((float)((qx + (dx > 0.0f ? 1 : 0)) * CELL) - px) * inv_dx;  // line parameter at the next x / z group boundary
+    float tmz = ((float)((qz + (dz > 0.0f ? 1 : 0)) * CELL) - pz) * inv_dz;
+    const float tdx = (float)CELL * fabsf(inv_dx), tdz = (float)CELL * fabsf(inv_dz);
     float t = 0.0f;
     for (int it = 0; it < 96; ++it) {
         if ((unsigned)qx >= (unsigned)qdim || (unsigned)qz >= (unsigned)qdim) return false;
         const float y_in = py + dy * t;  // lowest height of the line inside this group (it climbs)
-        if (y_in - 2.0f < (float)__ldg(&clear4[qx + qdim * qz])) return false;
+        if (y_in - 2.0f < (float)__ldg(&tops[qx + qdim * qz])) return false;
         if (y_in >= y_all) return true;  // above every occupied block of the world
         if (tmx < tmz) { t = tmx; tmx += tdx; qx += sx; }
         else { t = tmz; tmz += tdz; qz += sz; }
         if (t > t_stop) return true;
     }
     return false;
+}
+
+// The coarse groups are tried first (a handful of cells for the whole reach: rays well above the terrain), the 4x4
+// groups only when that fails.
+__device__ __noinline__ bool sky_sealed(const uint16_t *__restrict__ clear4, const uint16_t *__restrict__ clear64, int dim, int y_clear,
+                                        float px, float py, float pz, float dx, float dy, float dz, int trips_left) {
+    const float inv_dx = 1.0f / dx, inv_dz = 1.0f / dz;
+    // each trip crosses one block boundary, so after n trips the line has covered about n blocks in L1
+    const float t_stop = (float)(trips_left + 4) / (fabsf(dx) + fabsf(dy) + fabsf(dz));
+    const float y_all = (float)y_clear + 2.0f;
+    if (sky_walk<64>(clear64, (dim + 63) >> 6, y_all, px, py, pz, dx, dy, dz, inv_dx, inv_dz, t_stop)) return true;
+    return sky_walk<4>(clear4, dim >> 2, y_all, px, py, pz, dx, dy, dz, inv_dx, inv_dz, t_stop);
 }
 
 // One DDA step (map.glsl:157-162), hand-scheduled and branch-free: 6 ops for t, 3 compares, min3,
@@ -600,7 +610,7 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
             seg_end = min(max_steps > 64 ? (seg_end == 4 ? 32 : 2 * seg_end) : 2 * seg_end + 4, max_steps);
             // ---- sealed-ray test (c), all candidate lanes of the warp at once ----------------
             if (climbs && limit < kDead && big &&
-                sky_sealed(w.clear4, w.dim, w.y_clear, ((float)gx + wx) * 0.125f, ((float)gy + wy) * 0.125f, ((float)gz + wz) * 0.125f, dx, dy, dz, max_steps - trip)) {
+                sky_sealed(w.clear4, w.clear64, w.dim, w.y_clear, ((float)gx + wx) * 0.125f, ((float)gy + wy) * 0.125f, ((float)gz + wz) * 0.125f, dx, dy, dz, max_steps - trip)) {
                 out.trips = (uint32_t)max_steps;  // iteration-cap miss (map.glsl:167)
                 out.px = out.py = out.pz = 0xFFFFFFFFu;
                 limit = kDead;

@@ -62,6 +62,7 @@ struct uvt_ctx {
     bool incremental_ok = false;        // the last full commit left everything uvt_world_commit_region needs
     int32_t y_clear = 0;            // max occupied block y + 1 (every block at or above is empty)
     uint16_t *d_clear4 = nullptr;   // [(dim/4)^2] dilated column-group tops for sky_sealed()
+    uint16_t *d_clear64 = nullptr;  // [ceil(dim/64)^2] their maxima over 64x64-block groups
     uint8_t *d_dense = nullptr;     // [dim^3] dense block grid (nullptr: not built — too large or disabled)
     bool dense_valid = false;
     bool world_committed = false;
@@ -274,6 +275,7 @@ WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     a.w.y_clear = c->y_clear;
     a.w.dim = (int32_t)c->dim;
     a.w.clear4 = c->d_clear4;
+    a.w.clear64 = c->d_clear64;
     a.w.dense = c->d_dense;
     a.w.bricks8 = c->d_bricks8;
     a.w.mat_word = c->d_mat_word;
@@ -440,6 +442,9 @@ int upload_material_lut(uvt_ctx *c, uint32_t *d_keys, uint8_t *d_vals) {
 int finish_tops(uvt_ctx *c, unsigned int *d_max) {
     const int nq = (int)((c->dim / 4) * (c->dim / 4));
     quad_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_tops32, c->d_clear4, (int)c->dim);
+    const int nc = (int)(((c->dim + 63) / 64) * ((c->dim + 63) / 64));
+    coarse_clear_kernel<<<(nc + 127) / 128, 128, 0, c->stream>>>(c->d_clear4, c->d_clear64, (int)c->dim);
+    c->launches++;
     UVT_CUDA(c, cudaMemsetAsync(d_max, 0, 4, c->stream));
     max_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, nq, d_max);
     c->launches += 2;
@@ -640,7 +645,7 @@ void uvt_destroy(uvt_ctx *c) {
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
     cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
     cudaFree(c->d_rowmask); cudaFree(c->d_brick_chunk); cudaFree(c->d_tops32); cudaFree(c->d_scratch);
-    cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]);
+    cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]); cudaFree(c->d_clear64);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
     cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame);
     for (int i = 0; i < 4; ++i)
@@ -738,7 +743,8 @@ int uvt_pipeline_dispatch(uvt_pipeline *p, uint32_t gx, uint32_t gy, uint32_t gz
 static int reset_world(uvt_ctx *c, uint32_t dim) {
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
-    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32);
+    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32); cudaFree(c->d_clear64);
+    c->d_clear64 = nullptr;
     cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]);
     c->d_field = c->d_field_tmp[0] = c->d_field_tmp[1] = nullptr;
     c->d_dense = nullptr;
@@ -760,6 +766,7 @@ static int reset_world(uvt_ctx *c, uint32_t dim) {
     UVT_CUDA(c, cudaMalloc(&c->d_chunks, n_chunks * 4));
     UVT_CUDA(c, cudaMalloc(&c->d_chunks2, (size_t)(c->cd + 1) * (c->cd + 1) * (c->cd + 1) * 4));
     UVT_CUDA(c, cudaMalloc(&c->d_clear4, (size_t)(dim / 4) * (dim / 4) * 2));
+    UVT_CUDA(c, cudaMalloc(&c->d_clear64, (size_t)((dim + 63) / 64) * ((dim + 63) / 64) * 2));
     return UVT_OK;
 }
 
