@@ -510,6 +510,57 @@ def test_fast_path_vs_verbatim_kernel_many_poses(uvt, oracle, w1):
     ctx.set_layout("compact")
 
 
+def test_lattice_and_diagonal_rays_round_up_carries(uvt, oracle, w1):
+    """Cameras on lattice points looking along face and space diagonals: many rays cross block edges and corners exactly,
+    `within` rounds up to the step size (the carry of the free-trip bound) and t ties are common.  The conditional last
+    free trip must fall back to the generic loop there: fast path == verbatim kernel == oracle."""
+    ctx, sc = w1
+    ctx.resize(256, 144)
+    n_checked = 0
+    for (pos, pitch, yaw, fov) in [((256.0, 40.0, 256.0), 0.0, np.pi / 4, np.pi / 2),
+                                   ((256.0, 40.0, 256.0), 0.0, 3 * np.pi / 4, np.pi / 2),
+                                   ((128.0, 64.0, 128.0), float(np.arctan(1 / np.sqrt(2))), np.pi / 4, 1.2),
+                                   ((128.0, 64.0, 128.0), -float(np.arctan(1 / np.sqrt(2))), 5 * np.pi / 4, 1.2),
+                                   ((300.0, 30.0, 200.0), 0.0, 0.0, np.pi / 2),
+                                   ((300.5, 30.5, 200.5), 0.0, np.pi / 2, 2 * float(np.arctan(0.5))),
+                                   ((64.0, 80.0, 64.0), -np.pi / 4, np.pi / 4, np.pi / 2),
+                                   ((8.0, 24.0, 8.0), 0.25, np.pi / 4, np.pi / 2)]:
+        cam = oracle.make_camera(pos, pitch_yaw_matrix(uvt, pitch, yaw), fov=fov)
+        ctx.set_layout("compact")
+        a = gpu_render(ctx, cam)
+        ctx.set_layout("reference")
+        b = gpu_render(ctx, cam)
+        ctx.set_layout("compact")
+        assert np.array_equal(a["hits"].view(np.uint8), b["hits"].view(np.uint8)), (pos, pitch, yaw)
+        for k in ("albedo", "normal", "illumination", "frame"):
+            assert np.array_equal(a[k], b[k]), (pos, k)
+        assert_primary_parity(a, oracle.render(sc.oracle_world, cam, 256, 144))
+        n_checked += 1
+    assert n_checked == 8
+
+
+def test_degenerate_camera_rays_take_the_generic_loop_on_the_compact_layout(uvt, oracle, w1):
+    """A camera matrix that squeezes the x axis to 1e-36 gives every ray a non-finite-ish reciprocal (|1/dir.x| > 1e30):
+    those lanes leave the fast path for the generic loop, which must read the compact layout (clearance bytes of empty
+    blocks are not materials) exactly like the reference layout."""
+    ctx, sc = w1
+    ctx.resize(128, 72)
+    m = pitch_yaw_matrix(uvt, 0.3, 0.7).reshape(4, 4).copy()
+    m[0, :] *= np.float32(1e-36)
+    for pos in ((256.0, 40.0, 256.0), (100.5, 30.25, 300.75)):
+        cam = oracle.make_camera(pos, m.reshape(16))
+        ctx.set_layout("compact")
+        a = gpu_render(ctx, cam)
+        ctx.set_layout("reference")
+        b = gpu_render(ctx, cam)
+        ctx.set_layout("compact")
+        assert np.array_equal(a["hits"].view(np.uint8), b["hits"].view(np.uint8))
+        for k in ("albedo", "normal", "illumination", "frame"):
+            assert np.array_equal(a[k], b[k]), k
+        assert_primary_parity(a, oracle.render(sc.oracle_world, cam, 128, 72))
+        assert (a["hits"]["exit_kind"] == 0).any()   # the view does reach terrain
+
+
 # ---- incremental publish (SURVEY §8 f2): uvt_world_commit_region / uvt_world_set_voxel / bind() of a dirty box ------
 def _fresh_full_commit(uvt, sc, tmp_path, **ctx_kw):
     """A second ctx holding the same host world, published by one full commit."""

@@ -68,13 +68,15 @@ struct WorldRef {
     __device__ __forceinline__ uint32_t block_word(uint32_t block) const { return block; }
 };
 
+constexpr uint32_t kMatLimit = 224;  // brick bytes >= kMatLimit encode empty blocks (kMatLimit + free trips, see trace_map_fast)
+
 // B200 layout (DESIGN.md "Data layout in HBM"): u32 chunk table, 8-bit material bricks
 // (512 B instead of 2 KiB), per-material 512-bit sub-voxel occupancy masks staged in shared
 // memory, colours and block words resolved only at the hit.
 struct WorldCompact {
     const uint32_t *__restrict__ chunks;    // reference encoding (0 = empty else brick+1); generic path only
     const uint32_t *__restrict__ chunks2;   // [(cd+1)^3] fast-path encoding, see trace_map_fast
-    const uint8_t *__restrict__ bricks8;    // [n_bricks][512], value = material id (0 = empty)
+    const uint8_t *__restrict__ bricks8;    // [slots][512], value = material id, or kMatLimit + free trips for an empty block
     const uint32_t *__restrict__ mat_word;  // [256] material id -> block word
     const uint32_t *__restrict__ mat_color; // [256][512] material id -> model texels
     const uint32_t *smem_masks;             // [kSmemMaskMats][16] shared-memory copy of the first occupancy masks
@@ -98,7 +100,8 @@ struct WorldCompact {
         const uint32_t idx = __ldg(&chunks[cx + cd * (cy + cz * cd)]);
         if (idx == 0) return 0;
         chunk_hit = true;
-        return __ldg(&bricks8[(size_t)(idx - 1) * 512u + (bx & 7u) + (((bz & 7u) << 3) + (by & 7u)) * 8u]);
+        const uint32_t b8 = __ldg(&bricks8[(size_t)(idx - 1) * 512u + (bx & 7u) + (((bz & 7u) << 3) + (by & 7u)) * 8u]);
+        return b8 < kMatLimit ? b8 : 0u;  // empty blocks carry their clearance
     }
     __device__ __forceinline__ bool sub_solid(uint32_t mat, uint32_t px, uint32_t py, uint32_t pz, uint32_t &color) const {
         const uint32_t bit = (px & 7u) + ((py & 7u) << 3) + ((pz & 7u) << 6);
@@ -380,7 +383,6 @@ __device__ __forceinline__ void dda_step_last(int &gx, int &gy, int &gz, float &
 //
 // Rays with non-finite reciprocals or origins beyond 2^20 sub-voxels take the generic path,
 // whose corner-case behaviour (NaN ordering, saturation) is the specification.
-constexpr uint32_t kMatLimit = 224;  // brick bytes >= kMatLimit encode empty blocks
 constexpr int kDead = 0x40000000;    // `limit` of a lane without a live ray
 
 // Must be called by ALL 32 lanes of a warp (it uses full-mask warp reductions); `active` = this lane has a ray.
