@@ -811,3 +811,39 @@ def test_incremental_commit_random_edit_sequences(uvt, oracle, scene_factory, tm
                     assert_primary_parity(a, oracle.render(world, cam, 96, 64))
             finally:
                 ctx2.close()
+
+
+def test_caller_owned_staging(uvt, oracle, world64, models):
+    """uvt_world_use_staging: the ctx publishes a world that lives in the caller's (pageable) arrays; growing the pool
+    on the caller's side is announced with dim = 0."""
+    import ctypes
+    L = uvt._native.load()
+    with uvt.Context(0, map_dim=64, hit_buffer=True) as ctx:
+        atlas = uvt.voxel.VoxelModelAtlas.init(ctx)
+        for m in models:
+            atlas.append_model(m)
+        chunks = world64.chunks.copy()
+        bricks = world64.bricks.copy()
+        ctx.check(L.uvt_world_use_staging(ctx.handle, 64, chunks.ctypes.data, bricks.ctypes.data, bricks.shape[0]))
+        assert L.uvt_world_grow(ctx.handle, 4 * bricks.shape[0], ctypes.byref(ctypes.c_void_p())) == uvt._native.UVT_ERR_INVALID
+        ctx.check(L.uvt_world_commit(ctx.handle, world64.n_bricks))
+        ctx.resize(96, 64)
+        cam = oracle.make_camera((35.5, 20.0, 4.0))
+        a = gpu_render(ctx, cam)
+        assert_primary_parity(a, oracle.render(world64.oracle_world, cam, 96, 64))
+        # the caller grows its pool, adds a brick of rock in an empty chunk and publishes only that box
+        bigger = np.zeros((bricks.shape[0] + 8, 512), dtype=np.uint32)
+        bigger[:bricks.shape[0]] = bricks
+        n = world64.n_bricks
+        cz, cy, cx = 1, 2, 4                      # chunk (4, 2, 1): just above the water of a 64^3 world, straight ahead of the camera
+        assert chunks.reshape(8, 8, 8)[cz, cy, cx] == 0
+        chunks.reshape(8, 8, 8)[cz, cy, cx] = n + 1
+        bigger[n, :] = uvt.voxel.Voxel(11, True)
+        ctx.check(L.uvt_world_use_staging(ctx.handle, 0, None, bigger.ctypes.data, bigger.shape[0]))
+        lo = (ctypes.c_uint32 * 3)(32, 16, 8)
+        hi = (ctypes.c_uint32 * 3)(39, 23, 15)
+        ctx.check(L.uvt_world_commit_region(ctx.handle, n + 1, ctypes.byref(lo), ctypes.byref(hi)))
+        b = gpu_render(ctx, cam)
+        world = oracle.World(64, chunks.copy(), bigger[:n + 1].copy(), world64.oracle_world.atlas)
+        assert_primary_parity(b, oracle.render(world, cam, 96, 64))
+        assert not np.array_equal(a["hits"]["block"], b["hits"]["block"])

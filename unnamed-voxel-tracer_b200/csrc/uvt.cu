@@ -842,6 +842,7 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
     for (size_t i = 0; i < n_chunks; ++i)
         if (c->h_chunks[i] > n_bricks) return set_error(c, UVT_ERR_INVALID, "chunk entry %zu names brick %u >= n_bricks %zu", i, c->h_chunks[i] - 1, n_bricks);
 
+    c->world_committed = false;  // until every step below has succeeded
     const size_t cap = std::max<size_t>(n_bricks, 1);
     if (cap > c->d_brick_capacity) {
         cudaFree(c->d_bricks);
@@ -887,9 +888,21 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
 // blocks is refreshed in place: the bricks of the box, the clearances and dense-grid bytes of every chunk
 // within two chunks of it (clearances look kClearCap = 16 blocks far), the column tops under it; a new brick
 // additionally refreshes the chunk distance field and gives newly adjacent empty chunks a virtual brick.
+static int commit_region_impl(uvt_ctx *c, size_t n_bricks, const uint32_t lo[3], const uint32_t hi[3]);
+
 int uvt_world_commit_region(uvt_ctx *c, size_t n_bricks, const uint32_t lo[3], const uint32_t hi[3]) {
     if (!c) return UVT_ERR_INVALID;
     UVT_ENTER(c);
+    const int rc = commit_region_impl(c, n_bricks, lo, hi);
+    if (rc != UVT_OK && rc != UVT_ERR_INVALID) {
+        // a device-side failure half way leaves the derived layout inconsistent: nothing may be traced until a full commit succeeds
+        c->incremental_ok = false;
+        c->world_committed = false;
+    }
+    return rc;
+}
+
+static int commit_region_impl(uvt_ctx *c, size_t n_bricks, const uint32_t lo[3], const uint32_t hi[3]) {
     UVT_REQUIRE(c, c->h_chunks && c->h_bricks, "no world allocated");
     UVT_REQUIRE(c, lo && hi, "NULL box");
     UVT_REQUIRE(c, n_bricks <= c->h_capacity, "n_bricks exceeds the pool capacity");
