@@ -223,13 +223,23 @@ __device__ __forceinline__ void trace_map(const World &w, float ox, float oy, fl
 }
 
 // ---- conservative "nothing ahead" test for climbing rays -------------------------------------
-// A ray with dir.y > 0 whose straight line stays at least two blocks above every occupied block of the
+// A ray with dir.y > 0 whose straight line stays at least kSkyMargin (one block) above every occupied block of the
 // 4x4-block column groups it passes over (each grown by one block sideways, clear4) cannot meet a
 // non-empty block: the reference DDA follows that line to within a fraction of a block (0.999 resets,
 // fp32 rounding) and looks up `pos` at most one block beside it.  The test walks the column groups with
 // a 2-D DDA until the line has covered more blocks (L1) than the remaining trips can cross, or has risen
 // above the whole world.  It decides only WHETHER lookups can be skipped, never a hit, so it needs no
 // bit-exact arithmetic.  (px, py, pz) in blocks, d = the ray direction with zero components patched.
+#ifndef UVT_SKY_MARGIN
+#define UVT_SKY_MARGIN 1.0f
+#endif
+// Blocks of air demanded between the line and the tops under it.  What is needed: the state of a climbing ray is
+// the line's point at its parameter, exact in y (resets of an axis travelled upwards are exact) and up to 0.001 block
+// per trip (the 0.999 resets) ahead along the horizontal axes; a lookup names the block of that point or, when `within`
+// undershoots zero, the one behind it — within one block sideways (the groups are grown by one block) and never a row
+// below the line's.  So y_in >= top would do in exact arithmetic; one block covers the fp32 slack of this test with room.
+constexpr float kSkyMargin = UVT_SKY_MARGIN;
+
 // CELL = blocks per column group: 4 (clear4) or 64 (clear64, the maximum of clear4 over 16x16 groups).
 template <int CELL>
 __device__ __forceinline__ bool sky_walk(const uint16_t *__restrict__ tops, int qdim, float y_all, float px, float py, float pz,
@@ -243,7 +253,7 @@ __device__ __forceinline__ bool sky_walk(const uint16_t *__restrict__ tops, int 
     for (int it = 0; it < 96; ++it) {
         if ((unsigned)qx >= (unsigned)qdim || (unsigned)qz >= (unsigned)qdim) return false;
         const float y_in = py + dy * t;  // lowest height of the line inside this group (it climbs)
-        if (y_in - 2.0f < (float)__ldg(&tops[qx + qdim * qz])) return false;
+        if (y_in - kSkyMargin < (float)__ldg(&tops[qx + qdim * qz])) return false;
         if (y_in >= y_all) return true;  // above every occupied block of the world
         if (tmx < tmz) { t = tmx; tmx += tdx; qx += sx; }
         else { t = tmz; tmz += tdz; qz += sz; }
@@ -259,7 +269,7 @@ __device__ __noinline__ bool sky_sealed(const uint16_t *__restrict__ clear4, con
     const float inv_dx = 1.0f / dx, inv_dz = 1.0f / dz;
     // each trip crosses one block boundary, so after n trips the line has covered about n blocks in L1
     const float t_stop = (float)(trips_left + 4) / (fabsf(dx) + fabsf(dy) + fabsf(dz));
-    const float y_all = (float)y_clear + 2.0f;
+    const float y_all = (float)y_clear + kSkyMargin;
     if (sky_walk<64>(clear64, (dim + 63) >> 6, y_all, px, py, pz, dx, dy, dz, inv_dx, inv_dz, t_stop)) return true;
     return sky_walk<4>(clear4, dim >> 2, y_all, px, py, pz, dx, dy, dz, inv_dx, inv_dz, t_stop);
 }
@@ -371,7 +381,7 @@ __device__ __forceinline__ void dda_step_last(int &gx, int &gy, int &gz, float &
 //    been, so it is retired at once: (a) trip + 1 + n_free >= maxSteps, or (b) the ray climbs
 //    (dir.y > 0), its block row is above every occupied block of the world, and no map face in its
 //    direction of travel is within maxSteps + 2 blocks (one block per trip at most), or (c) the ray
-//    climbs and sky_sealed() proves its line stays two blocks above the terrain it passes over.
+//    climbs and sky_sealed() proves its line stays a block above the terrain it passes over.
 //    (c) is tried by the whole warp together at trips 4, 32, 64, 128 (a failed test is cheap).  Sky
 //    and sun-shadow rays stop marching as soon as they clear the terrain.  Only a lookup that found an EMPTY block can seal
 //    (the current trip's own block must still be tested).  (COUNT == 1 never seals: exact counters.)
