@@ -298,3 +298,53 @@ def test_camera_uniform_data_layout(uvt):
     assert np.isclose(cam.pitch, np.pi / 2)
     cam.incrementFov(100)
     assert np.isclose(cam.fov, 2.4)
+
+
+def test_vox_parser_survives_mutations(uvt):
+    """Truncations, byte flips and absurd counts in an otherwise valid file end in a parsed file or a UvtError, never
+    in a crash or an out-of-bounds read (the parser works on caller memory: uvt_vox_parse(data, size))."""
+    rng = np.random.default_rng(7)
+    pal = [(0xFF000000 | (i * 0x010203)) & 0xFFFFFFFF for i in range(256)]
+    base = make_vox([((8, 8, 8), [(int(a), int(b), int(c), 1 + int(d)) for a, b, c, d in rng.integers(0, 8, (40, 4))]),
+                     ((8, 8, 8), [(1, 2, 3, 4)])], pal, extra_before_rgba=[b"nTRN", b"LAYR"], imap=list(range(256)))
+    n_ok = n_err = 0
+    cases = [base[:k] for k in range(0, len(base), 7)]
+    for _ in range(300):
+        b = bytearray(base)
+        for _ in range(int(rng.integers(1, 6))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        cases.append(bytes(b))
+    # chunk sizes and voxel counts far beyond the buffer
+    for off in (12, 16, 24, 28, 36, 40, 44):
+        b = bytearray(base)
+        b[off:off + 4] = struct.pack("<I", 0xFFFFFFF0)
+        cases.append(bytes(b))
+    for data in cases:
+        try:
+            models, palette = uvt.voxel.parse_vox(data)
+            assert len(palette) == 256
+            for size, vox in models:
+                assert vox.shape[1] == 4
+            n_ok += 1
+        except uvt.UvtError:
+            n_err += 1
+    assert n_ok > 0 and n_err > 0
+
+
+def test_world_dump_rejects_malformed_files(uvt, tmp_path, world64):
+    good = tmp_path / "w.uvtw"
+    bm = uvt.voxel.VoxelBrickmap.init(64, 8, None)
+    uvt.procgen.procgen(64, bm)
+    bm.save(str(good))
+    raw = good.read_bytes()
+    for name, data in (("magic", b"XXXX" + raw[4:]), ("version", raw[:4] + struct.pack("<I", 9) + raw[8:]),
+                       ("truncated_header", raw[:10]), ("truncated_chunks", raw[:16 + 100]), ("truncated_bricks", raw[:-1000]),
+                       ("empty", b"")):
+        p = tmp_path / f"{name}.uvtw"
+        p.write_bytes(data)
+        with pytest.raises(uvt.UvtError):
+            uvt.voxel.VoxelBrickmap.load(str(p), None)
+    with pytest.raises(uvt.UvtError):
+        uvt.voxel.VoxelBrickmap.load(str(tmp_path / "missing.uvtw"), None)
+    back = uvt.voxel.VoxelBrickmap.load(str(good), None)
+    assert back.n_bricks == bm.n_bricks and np.array_equal(back.chunks(), bm.chunks())
