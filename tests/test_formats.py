@@ -339,7 +339,8 @@ def test_world_dump_rejects_malformed_files(uvt, tmp_path, world64):
     raw = good.read_bytes()
     for name, data in (("magic", b"XXXX" + raw[4:]), ("version", raw[:4] + struct.pack("<I", 9) + raw[8:]),
                        ("truncated_header", raw[:10]), ("truncated_chunks", raw[:16 + 100]), ("truncated_bricks", raw[:-1000]),
-                       ("empty", b"")):
+                       ("huge_dim", raw[:8] + struct.pack("<I", 0xFFFFFFF8) + raw[12:]), ("odd_dim", raw[:8] + struct.pack("<I", 65) + raw[12:]),
+                       ("huge_n_bricks", raw[:12] + struct.pack("<I", 0xFFFFFFFF) + raw[16:]), ("empty", b"")):
         p = tmp_path / f"{name}.uvtw"
         p.write_bytes(data)
         with pytest.raises(uvt.UvtError):

@@ -86,7 +86,7 @@ int uvt_brickmap_create_group(uvt_group *group, uint32_t dim, uvt_brickmap **out
 }
 
 static int brickmap_create(uvt_ctx *ctx, uvt_group *group, uint32_t dim, uvt_brickmap **out) {
-    if (!out || dim == 0 || dim % kChunk != 0) return UVT_ERR_INVALID;
+    if (!out || dim == 0 || dim % kChunk != 0 || dim > 4096) return UVT_ERR_INVALID;  // 4096: the bound of uvt_world_alloc
     uvt_brickmap *bm = new (std::nothrow) uvt_brickmap;
     if (!bm) return UVT_ERR_OOM;
     bm->ctx = ctx;
@@ -191,6 +191,16 @@ int uvt_brickmap_load(uvt_ctx *ctx, const char *path, uvt_brickmap **out) {
     if (!f) return UVT_ERR_IO;
     uint32_t hdr[4];
     if (std::fread(hdr, sizeof hdr, 1, f) != 1 || hdr[0] != 0x57545655u || hdr[1] != 1u) { std::fclose(f); return UVT_ERR_FORMAT; }
+    if (hdr[2] == 0 || hdr[2] % kChunk != 0 || hdr[2] > 4096) { std::fclose(f); return UVT_ERR_FORMAT; }
+    {   // the header must agree with the file: nothing is allocated for a size the file cannot back
+        const size_t cdim = hdr[2] / kChunk, want = sizeof hdr + cdim * cdim * cdim * sizeof(uint32_t) + (size_t)hdr[3] * kBrickWords * sizeof(uint32_t);
+        if (std::fseek(f, 0, SEEK_END) != 0) { std::fclose(f); return UVT_ERR_IO; }
+        const long size = std::ftell(f);
+        if (size < 0 || (size_t)size < want || (size_t)hdr[3] > cdim * cdim * cdim || std::fseek(f, (long)sizeof hdr, SEEK_SET) != 0) {
+            std::fclose(f);
+            return UVT_ERR_FORMAT;
+        }
+    }
     uvt_brickmap *bm = nullptr;
     int rc = uvt_brickmap_create(ctx, hdr[2], &bm);
     if (rc != UVT_OK) { std::fclose(f); return rc; }
