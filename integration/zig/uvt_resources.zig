@@ -76,7 +76,9 @@ pub fn VoxelBrickmap(comptime dim: comptime_int, comptime chsize: comptime_int) 
             return c.uvt_brickmap_is_walkable(self.handle, @intCast(x), @intCast(y), @intCast(z)) != 0;
         }
 
-        /// GL mappings are live; CUDA staging is published here, and only when something changed.
+        /// GL mappings are live; CUDA staging is published here.  The library tracks the box of blocks written through
+        /// set() since the last bind and publishes only that (uvt_world_commit_region, a fraction of a millisecond);
+        /// the flag below merely skips the call on clean frames.
         pub fn bind(self: *@This(), _: u32) void {
             if (!self.dirty) return;
             uvt.check(c.uvt_brickmap_bind(self.handle)) catch {};
