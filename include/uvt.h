@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UVT_ABI_VERSION 1
+#define UVT_ABI_VERSION 2
 
 typedef enum uvt_status {
     UVT_OK = 0,
@@ -63,8 +63,8 @@ typedef enum uvt_layout {
 } uvt_layout;
 
 typedef enum uvt_scheduler {
-    UVT_SCHED_POOL = 0, /* per-CTA ray pool, compacted between trip phases */
-    UVT_SCHED_TILE = 1  /* one pixel per thread for the whole traversal (default: measured faster) */
+    UVT_SCHED_TILE = 0, /* one pixel per thread for the whole traversal (default — also what a zero-initialised uvt_params selects) */
+    UVT_SCHED_POOL = 1  /* per-CTA ray pool, compacted between trip phases (opt-in; measured slower) */
 } uvt_scheduler;
 
 void uvt_default_params(uvt_params *p);

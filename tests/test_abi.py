@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(uvt):
 
 def test_abi_version_and_struct_sizes(uvt):
     N = uvt._native
-    assert N.load().uvt_abi_version() == 1
+    assert N.load().uvt_abi_version() == 2
     assert N.CAMERA_DTYPE.itemsize == 96     # camera.zig:12-16 / std140
     assert N.CAMERA_DTYPE.fields["cam_mat"][1] == 16 and N.CAMERA_DTYPE.fields["fov"][1] == 80
     assert N.HIT_DTYPE.itemsize == 28

@@ -340,7 +340,11 @@ def test_world_dump_rejects_malformed_files(uvt, tmp_path, world64):
     for name, data in (("magic", b"XXXX" + raw[4:]), ("version", raw[:4] + struct.pack("<I", 9) + raw[8:]),
                        ("truncated_header", raw[:10]), ("truncated_chunks", raw[:16 + 100]), ("truncated_bricks", raw[:-1000]),
                        ("huge_dim", raw[:8] + struct.pack("<I", 0xFFFFFFF8) + raw[12:]), ("odd_dim", raw[:8] + struct.pack("<I", 65) + raw[12:]),
-                       ("huge_n_bricks", raw[:12] + struct.pack("<I", 0xFFFFFFFF) + raw[16:]), ("empty", b"")):
+                       ("huge_n_bricks", raw[:12] + struct.pack("<I", 0xFFFFFFFF) + raw[16:]), ("empty", b""),
+                       # chunk entries index the brick pool unchecked in get/set: one past the pool, far past it, and a shared brick
+                       ("bad_chunk_entry", raw[:16] + struct.pack("<I", bm.n_bricks + 1) + raw[20:]),
+                       ("wild_chunk_entry", raw[:16] + struct.pack("<I", 0x20000001) + raw[20:]),
+                       ("shared_brick", raw[:16] + raw[16:20] + raw[16:20] + raw[24:])):
         p = tmp_path / f"{name}.uvtw"
         p.write_bytes(data)
         with pytest.raises(uvt.UvtError):

@@ -21,7 +21,7 @@ UVT_OK = 0
 UVT_ERR_INVALID, UVT_ERR_CUDA, UVT_ERR_NO_DEVICE, UVT_ERR_OOM, UVT_ERR_FORMAT, UVT_ERR_IO = -1, -2, -3, -4, -5, -6
 UVT_FLAG_HIT_BUFFER, UVT_FLAG_ENTITIES, UVT_FLAG_NO_DENSE, UVT_FLAG_FUSED_FRAME = 1, 2, 4, 8
 UVT_LAYOUT_COMPACT, UVT_LAYOUT_REFERENCE = 0, 1
-UVT_SCHED_POOL, UVT_SCHED_TILE = 0, 1
+UVT_SCHED_TILE, UVT_SCHED_POOL = 0, 1
 UVT_PIPELINE_PRIMARY, UVT_PIPELINE_SECONDARY, UVT_PIPELINE_EDIT, UVT_PIPELINE_BLIT = 0, 1, 2, 3
 UVT_BUF_ALBEDO, UVT_BUF_NORMAL, UVT_BUF_POSITION, UVT_BUF_ILLUMINATION, UVT_BUF_FRAME, UVT_BUF_HIT = range(6)
 

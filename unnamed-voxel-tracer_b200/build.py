@@ -21,12 +21,11 @@ SOURCES = [
     os.path.join(CSRC, "host", "atlas.cpp"),
     os.path.join(CSRC, "host", "camera.cpp"),
 ]
-HEADERS = [
-    os.path.join(CSRC, "trace.cuh"),
-    os.path.join(CSRC, "kernels.cuh"),
-    os.path.join(ROOT, "include", "uvt.h"),
-    os.path.join(ROOT, "include", "uvt_host.h"),
-]
+import glob
+
+# everything a source may include: an edit to any of them makes the library stale
+HEADERS = sorted(glob.glob(os.path.join(CSRC, "**", "*.cuh"), recursive=True) + glob.glob(os.path.join(CSRC, "**", "*.h"), recursive=True) +
+                 glob.glob(os.path.join(ROOT, "include", "*.h")))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

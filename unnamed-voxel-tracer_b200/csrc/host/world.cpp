@@ -11,6 +11,7 @@
 #include <cstring>
 #include <algorithm>
 #include <new>
+#include <vector>
 
 struct uvt_brickmap {
     uvt_ctx *ctx = nullptr;
@@ -216,6 +217,16 @@ int uvt_brickmap_load(uvt_ctx *ctx, const char *path, uvt_brickmap **out) {
               std::fread(bm->bricks, sizeof(uint32_t) * kBrickWords, n_bricks, f) == n_bricks;
     std::fclose(f);
     if (!ok) { uvt_brickmap_destroy(bm); return UVT_ERR_FORMAT; }
+    {   // a chunk entry is 0 or brick + 1 of a brick the file holds, and no two chunks share a brick:
+        // get/set index the pool through these entries without a further check
+        std::vector<uint8_t> seen(n_bricks, 0);
+        for (size_t i = 0; i < n_chunks; ++i) {
+            const uint32_t e = bm->chunks[i];
+            if (e == 0) continue;
+            if (e > n_bricks || seen[e - 1]) { uvt_brickmap_destroy(bm); return UVT_ERR_FORMAT; }
+            seen[e - 1] = 1;
+        }
+    }
     bm->block_index = n_bricks;
     *out = bm;
     return UVT_OK;
@@ -278,7 +289,9 @@ int uvt_procgen(uvt_brickmap *world, uint32_t dim, float offset_x, float offset_
                 if (uvt_lcg_rand(&lcg) % 71 == 0)
                     if ((rc = uvt_brickmap_set(world, x, vh, z, uvt_voxel(7 + 5, 1))) != UVT_OK) return rc;
 
-                if (uvt_lcg_rand(&lcg) % 420 == 0 && x < 500 && z < 500 && x > 5 && z > 5)
+                // the reference's literal 500-block guard (procgen.zig:47); maps narrower than 503 blocks additionally keep the
+                // 3x3 canopy (x..x+2, z..z+2) inside the map, where the reference would index out of bounds (same at dim >= 503)
+                if (uvt_lcg_rand(&lcg) % 420 == 0 && x < 500 && z < 500 && x > 5 && z > 5 && x + 2 < dim && z + 2 < dim)
                     if ((rc = place_tree(&lcg, world, x, vh, z)) != UVT_OK) return rc;
             }
             (void)uvt_lcg_rand(&lcg);

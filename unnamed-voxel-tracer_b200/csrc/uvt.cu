@@ -115,6 +115,7 @@ struct uvt_ctx {
     cudaEvent_t ev[4][2] = {};
     bool ev_valid[4] = {false, false, false, false};
     uint32_t *d_sink = nullptr;
+    std::vector<void *> pinned;  // live uvt_alloc_pinned allocations
 };
 
 struct uvt_pipeline {
@@ -600,9 +601,19 @@ int uvt_create(const uvt_params *params, int device, uvt_ctx **out) {
     if (prop.major != 10)
         return set_error(nullptr, UVT_ERR_NO_DEVICE, "device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
 
+    uvt_params prm;
+    if (params) prm = *params;
+    else uvt_default_params(&prm);
+    // the same checks the setters make (uvt_set_max_steps, uvt_set_layout, uvt_set_scheduler)
+    if (prm.primary_max_steps > 65535u || prm.shadow_max_steps > 65535u || prm.edit_max_steps > 65535u)
+        return set_error(nullptr, UVT_ERR_INVALID, "step caps must fit 16 bits (uvt_hit.trips)");
+    if (prm.layout != UVT_LAYOUT_COMPACT && prm.layout != UVT_LAYOUT_REFERENCE) return set_error(nullptr, UVT_ERR_INVALID, "unknown layout %u", prm.layout);
+    if (prm.scheduler != UVT_SCHED_POOL && prm.scheduler != UVT_SCHED_TILE) return set_error(nullptr, UVT_ERR_INVALID, "unknown scheduler %u", prm.scheduler);
+    if (prm.map_dim != 0 && (prm.map_dim % 8u != 0 || prm.map_dim > 4096u)) return set_error(nullptr, UVT_ERR_INVALID, "map_dim must be a multiple of 8, at most 4096");
+    if (!(prm.epsilon == prm.epsilon)) return set_error(nullptr, UVT_ERR_INVALID, "epsilon is NaN");
+
     uvt_ctx *c = new uvt_ctx;
-    if (params) c->params = *params;
-    else uvt_default_params(&c->params);
+    c->params = prm;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     auto fail = [&](cudaError_t err, const char *what) {
@@ -642,6 +653,7 @@ void uvt_destroy(uvt_ctx *c) {
         if (c->snap_done[i]) cudaEventDestroy(c->snap_done[i]);
     }
     free_gbuffer(c);
+    for (void *p : c->pinned) cudaFreeHost(p);
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
     cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
     cudaFree(c->d_rowmask); cudaFree(c->d_brick_chunk); cudaFree(c->d_tops32); cudaFree(c->d_scratch);
@@ -1413,12 +1425,17 @@ int uvt_alloc_pinned(uvt_ctx *c, size_t bytes, void **out) {
     if (!c || !out) return UVT_ERR_INVALID;
     UVT_ENTER(c);
     UVT_CUDA(c, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    c->pinned.push_back(*out);  // owned by the ctx: whatever the caller has not freed goes with uvt_destroy
     return UVT_OK;
 }
 
 int uvt_free_pinned(uvt_ctx *c, void *p) {
     if (!c) return UVT_ERR_INVALID;
     UVT_ENTER(c);
+    if (!p) return UVT_OK;
+    auto it = std::find(c->pinned.begin(), c->pinned.end(), p);
+    UVT_REQUIRE(c, it != c->pinned.end(), "not a live uvt_alloc_pinned allocation of this ctx");
+    c->pinned.erase(it);
     UVT_CUDA(c, cudaFreeHost(p));
     return UVT_OK;
 }

@@ -75,7 +75,8 @@ class Context:
     # -- lifetime
     def close(self):
         if getattr(self, "handle", None):
-            self.L.uvt_destroy(self.handle)
+            self.L.uvt_destroy(self.handle)  # also frees the pinned buffers handed out by pinned_empty()
+            self._pinned = []
             self.handle = None
 
     def __enter__(self):
@@ -101,7 +102,7 @@ class Context:
         self.check(self.L.uvt_set_layout(self.handle, N.UVT_LAYOUT_COMPACT if layout == "compact" else N.UVT_LAYOUT_REFERENCE))
 
     def set_scheduler(self, scheduler):
-        """'pool' (per-CTA ray pool with phase-wise compaction, default) or 'tile' (one pixel per thread)."""
+        """'tile' (one pixel per thread, the default) or 'pool' (per-CTA ray pool with phase-wise compaction, opt-in)."""
         self.check(self.L.uvt_set_scheduler(self.handle, N.UVT_SCHED_POOL if scheduler == "pool" else N.UVT_SCHED_TILE))
 
     def effective_layout(self):
@@ -216,12 +217,23 @@ class Context:
         return out.reshape((layers,) + shape) if layers > 1 else out.reshape(shape)
 
     def pinned_empty(self, nbytes, dtype=np.uint8):
-        """numpy view over pinned host memory owned by the ctx (freed with it)."""
+        """numpy view over pinned host memory owned by the ctx: uvt_destroy frees whatever free_pinned() has not.
+        The view must not be used after close()."""
         p = ctypes.c_void_p()
         self.check(self.L.uvt_alloc_pinned(self.handle, nbytes, ctypes.byref(p)))
         self._pinned.append(p)
         buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype)
+
+    def free_pinned(self, arr):
+        """Release a pinned_empty() buffer early (the view is dead afterwards)."""
+        addr = arr.ctypes.data
+        for i, p in enumerate(self._pinned):
+            if p.value == addr:
+                self.check(self.L.uvt_free_pinned(self.handle, p))
+                del self._pinned[i]
+                return
+        raise UvtError(N.UVT_ERR_INVALID, "not a pinned_empty() buffer of this ctx")
 
     def readback_into(self, name, pinned):
         kind, _, _ = self._KINDS[name]
