@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|c5] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one frame of synthetic input (procgen world, fixed
-camera).  Default workload (N=1) is BASELINE.json configs[1]: the default procgen world (W1) at
-1920x1080, primary rays only, camera K0; metric = primary-ray throughput in Grays/s.
+camera).  Default workload is the configuration BASELINE.json's metric ("Grays/s and 4K frame ms") is
+quoted on, configs[2]: the 4x-scaled procgen world (W4) at 3840x2160, primary + shadow rays + shade,
+camera K1; metric = rays per second (primary + shadow), ms_per_step = the 4K frame time.  The same
+JSON line carries `also`: the 8K tiled frame (configs[3]) and the 1080p primary-only frame (configs[1]).
 
   value      device-timed throughput, inputs resident in HBM, CUDA events on the launch stream,
              L2 flushed (256 MiB memset) between timed steps; max over ranks.
@@ -15,9 +17,11 @@ camera).  Default workload (N=1) is BASELINE.json configs[1]: the default procge
              counters from the counting variant of the same kernel) / measured kernel time.
   cpu_baseline  the CPU oracle (port of the reference GLSL) on this box's host cores, rank 0, N=1.
 
-N > 1 (torchrun): the world is replicated; the default workload shards independent frames across
-ranks (weak scaling, no data-path collective).  --workload c4 is the 8K frame tiled across ranks
-with the NCCL band gather to rank 0 (strong scaling); --workload c5 the 256-pose sweep.
+N > 1 (torchrun): the world is replicated and the SAME frame is cut into interleaved 32-row bands
+across the ranks (strong scaling); the band exchange is inside the timed region: every rank's shade
+kernel stores its finished pixels straight into the presenting rank's frame over NVLink (--gather
+p2p, default) or the bands are gathered with NCCL (--gather nccl).  c2 at N > 1 runs one independent
+frame per rank (weak, no collective) and c5 shards the 256 poses.
 --impl reference times the reference's CPU implementation (the oracle port — the reference GLSL
 cannot run in this image) on the same config.
 """
@@ -39,8 +43,8 @@ WORKLOADS = {
     # name: (dim, W, H, shadows, description)
     "c1": (512, 1280, 720, True, "c1: W1 procgen(512) world, camera K0, 1280x720, primary + shadow rays + shade"),
     "c2": (512, 1920, 1080, False, "c2: W1 procgen(512) world, camera K0, 1920x1080, primary rays only"),
-    "c3": (2048, 3840, 2160, True, "c3: W4 procgen(2048) world, camera K1, 3840x2160, primary + shadow rays + shade"),
-    "c4": (512, 7680, 4320, True, "c4: W1 world, camera K1, 7680x4320 tiled in interleaved 32-row bands across ranks, NCCL gather to rank 0"),
+    "c3": (2048, 3840, 2160, True, "c3: W4 procgen(2048) world, camera K1, 3840x2160, primary + shadow rays + shade (the 4K frame)"),
+    "c4": (512, 7680, 4320, True, "c4: W1 world, camera K1, 7680x4320 tiled in interleaved 32-row bands across ranks, bands assembled on rank 0"),
     "c5": (2048, 1920, 1080, False, "c5: W4 world, 256 random poses at 1920x1080 sharded across ranks, primary rays"),
 }
 
@@ -48,10 +52,11 @@ WORKLOADS = {
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-also", action="store_true", help="skip the `also` sub-records (8K tiled frame, 1080p primary-only frame)")
     ap.add_argument("--layout", default="compact", choices=["compact", "reference"])
     ap.add_argument("--scheduler", default="tile", choices=["pool", "tile"],
                     help="tile = one pixel per thread (default); pool = per-CTA ray pool compacted between trip phases")
@@ -181,7 +186,8 @@ def run_reference(args):
     value = rays * args.steps / total / 1e9
     sample = f"{Ws}x{Hs} frame ({'full' if scale == 1 else '1/%d-area sample of' % (scale * scale)} {W}x{H}), {args.steps} steps"
     line = {"impl": "reference", "metric": "rays_per_second", "value": value, "unit": "Grays/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3 * (scale * scale), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3 * (scale * scale), "higher_is_better": True,
+            "scaling": "strong" if (args.gpus > 1 and args.workload in ("c1", "c3", "c4")) else "weak",
             "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic (procgen world, reference seeds)",
             "config": {"workload": desc, "rays_per_step": rays * scale * scale, "cpu_sample": sample},
             "cpu_baseline": {"value": value, "unit": "Grays/s", "cores": oracle.num_threads(), "kind": "port", "sample": sample},
@@ -192,31 +198,65 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    rank, local_rank, world = dist_env()
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    use_dist = world > 1
-    torch.cuda.set_device(local_rank)
-    if use_dist:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    uvt = importlib.import_module("unnamed-voxel-tracer_b200")
-    dim, W, H, shadows, desc = WORKLOADS[args.workload]
-    models = load_models()
+class Dist:
+    """torch.distributed plumbing (NCCL): barriers, max / sum over ranks, object broadcast."""
+
+    def __init__(self, torch, rank, local_rank, world):
+        self.torch, self.rank, self.local_rank, self.world = torch, rank, local_rank, world
+        self.on = world > 1
+        self.dev = f"cuda:{local_rank}"
+        if self.on:
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.on:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.dev)
+        if self.on:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def bcast(self, obj):
+        box = [obj]
+        if self.on:
+            self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def gather_obj(self, obj):
+        if not self.on:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def close(self):
+        if self.on:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, want_cpu_baseline):
+    """Build the workload on this rank, time `steps` passes of the hot path on the device, then the same through the
+    C ABI with host buffers (e2e).  Returns the record on rank 0 (None elsewhere)."""
+    rank, local_rank, world = D.rank, D.local_rank, D.world
+    dim, W, H, shadows, desc = WORKLOADS[workload]
+    sweep = workload == "c5"
+    tiled = world > 1 and workload in ("c1", "c3", "c4")   # one frame cut into bands across the ranks (strong scaling)
+    band = 32
 
     ctx = uvt.Context(local_rank, map_dim=dim, layout=args.layout, dense=not args.no_dense, fused_frame=args.fused_frame)
     ctx.set_scheduler(args.scheduler)
     stream = torch.cuda.Stream(device=local_rank)
     ctx.set_stream(stream.cuda_stream)  # launch on a torch stream so torch.cuda events / NCCL ordering see the work
     t0 = time.time()
-    uvt.scenes.build_world(ctx, dim, models)
+    bm, _ = uvt.scenes.build_world(ctx, dim, models)
     build_s = time.time() - t0
-
-    tiled = args.workload == "c4"
-    sweep = args.workload == "c5"
-    band = 32
     if tiled:
         ctx.set_partition(band, world, rank)
     ctx.resize(W, H)
@@ -226,45 +266,39 @@ def run_ours(args):
         my_poses = poses[lo:hi]
         cam = my_poses[0]
     else:
-        cam = uvt.scenes.camera_k0(dim) if args.workload in ("c1", "c2") else uvt.scenes.camera_k1(dim)
+        cam = uvt.scenes.camera_k0(dim) if workload in ("c1", "c2") else uvt.scenes.camera_k1(dim)
     ctx.set_camera(cam)
     ctx.enable_timing(True)
 
     rpp = uvt.tiles.rows_per_part(H, band, world) if tiled else H
-    gather_buf = None
     p2p = tiled and args.gather == "p2p"
-    shared_ptr = None
+    gather_buf = full_frame = shared_ptr = None
     if tiled:
-        gather_buf = torch.zeros((rpp, W), dtype=torch.int32, device=f"cuda:{local_rank}")
-        full_frame = torch.empty((H, W), dtype=torch.int32, device=f"cuda:{local_rank}") if rank == 0 else None
+        gather_buf = torch.zeros((rpp, W), dtype=torch.int32, device=D.dev)
+        full_frame = torch.empty((H, W), dtype=torch.int32, device=D.dev) if rank == 0 else None
         if p2p:
-            # the presenting rank owns the frame; every rank's kernels store their bands straight into it
-            box = [None]
+            # the presenting rank owns the frame; every rank's shade kernel stores its bands straight into it over NVLink
+            handle = None
             if rank == 0:
                 shared_ptr, handle = ctx.shared_frame_create()
-                box[0] = handle
-            if use_dist:
-                dist.broadcast_object_list(box, src=0)
+            handle = D.bcast(handle)
             if rank != 0:
-                shared_ptr = ctx.shared_frame_open(box[0])
+                shared_ptr = ctx.shared_frame_open(handle)
             ctx.bind_frame_target(shared_ptr, global_rows=True)
         else:
             ctx.bind_frame_target(gather_buf.data_ptr(), global_rows=False)
-
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
-    pinned = ctx.pinned_empty(W * ctx.local_rows() * 4, np.uint32)
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=D.dev)
 
     def device_step(i):
-        """One pass of the hot path, inputs resident.  Returns device ms measured with CUDA events on the launch stream."""
+        """One pass of the hot path, inputs resident.  Device ms from CUDA events on the launch stream."""
         if sweep:
             ctx.set_camera(my_poses[i % len(my_poses)])
         if shadows:
             ctx.dispatch_frame()
-            ms = ctx.last_pass_ms("frame")
-        else:
-            ctx.dispatch_primary()
-            ms = ctx.last_pass_ms("primary")
-        return ms
+            return ctx.last_pass_ms("frame"), ctx.last_pass_ms("primary")
+        ctx.dispatch_primary()
+        ms = ctx.last_pass_ms("primary")
+        return ms, ms
 
     def gather_step():
         with torch.cuda.stream(stream):
@@ -272,20 +306,10 @@ def run_ours(args):
             if rank == 0:
                 ctx.deinterleave(g.data_ptr(), full_frame.data_ptr(), rpp)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if use_dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # exact algorithmic bytes from the counting variant of the same kernels (outside the timed region)
     cp = ctx.count_pass("primary")
-    pixels_local = W * (ctx.local_rows() if tiled else H)
-    if tiled:
-        pixels_local = cp["rays"]
     alg_primary = 4 * (cp["t_in"] + cp["t_chunk"] + cp["t_block"]) + 24 * cp["rays"]
-    rays_step = cp["rays"]
-    alg_step = alg_primary
+    rays_step, alg_step = cp["rays"], alg_primary
     fetch = ctx.fetch_stats("primary") if ctx.effective_layout() == "compact" else None
     if shadows:
         ctx.dispatch_primary()
@@ -293,164 +317,217 @@ def run_ours(args):
         alg_step += 4 * (cs["t_in"] + cs["t_chunk"] + cs["t_block"]) + 24 * cs["rays"] + 20 * cs["early_out"] + 32 * cp["rays"]
         rays_step += cs["rays"]
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         device_step(i)
         if tiled and not p2p:
             gather_step()
-    barrier()
+    D.barrier()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.launch_count()
-    kernel_ms = []
-    gather_ms = []
-    barrier()
+    step_ms, primary_ms = [], []
+    D.barrier()
     wall0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         if flush is not None:
             with torch.cuda.stream(stream):
                 flush.fill_(i & 0xFF)  # evict L2 between timed iterations (untimed)
-        ms = device_step(i)
-        kernel_ms.append(ms)
         if tiled and not p2p:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
+            _, pm = device_step(i)
             gather_step()
             e1.record(stream)
             e1.synchronize()
-            gather_ms.append(e0.elapsed_time(e1))
-    barrier()
+            ms = e0.elapsed_time(e1)   # render + NCCL gather + reassembly, one bracket
+        else:
+            ms, pm = device_step(i)    # p2p: the band stores to rank 0 happen inside the shade kernel
+        step_ms.append(ms)
+        primary_ms.append(pm)
+    D.barrier()
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop()
 
     pass_ms = None
-    if shadows:  # per-pass device time of one frame (outside the timed region)
-        ctx.dispatch_primary(); ctx.dispatch_secondary(); ctx.shade(); ctx.sync()
+    if shadows:  # per-pass device time, averaged over the timed steps is not kept per pass: take one more frame
+        ctx.dispatch_frame(); ctx.sync()
         pass_ms = {k: ctx.last_pass_ms(k) for k in ("primary", "secondary", "shade")}
 
     verified = None
     if p2p:
         # the peer-stored frame must equal the NCCL-gathered one (checked outside the timed region)
         host_p2p = np.empty((H, W), np.uint32)
+        D.barrier()
         if rank == 0:
             ctx.read_device(shared_ptr, host_p2p)
         ctx.bind_frame_target(gather_buf.data_ptr(), global_rows=False)
         device_step(0)
         gather_step()
-        barrier()
+        D.barrier()
         if rank == 0:
             verified = bool(np.array_equal(full_frame.cpu().numpy().view(np.uint32), host_p2p))
         ctx.bind_frame_target(shared_ptr, global_rows=True)
 
-    step_ms_local = float(np.sum(kernel_ms) + np.sum(gather_ms))
-    t = torch.tensor([step_ms_local], dtype=torch.float64, device=f"cuda:{local_rank}")
-    totals = torch.tensor([float(rays_step), float(alg_step)], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if use_dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(totals, op=dist.ReduceOp.SUM)
-    total_ms = float(t.item())
-    rays_all, alg_all = float(totals[0].item()), float(totals[1].item())
-    value = rays_all * args.steps / (total_ms * 1e-3) / 1e9
+    # a step ends when its slowest rank ends: per-step max over ranks, then the sum over the timed steps
+    per_step_max = D.reduce(step_ms, "max")
+    total_ms = float(np.sum(per_step_max))
+    rays_all, alg_all = D.reduce([float(rays_step), float(alg_step)], "sum")
+    value = rays_all * steps / (total_ms * 1e-3) / 1e9
 
-    # ---- e2e: the same metric through the C ABI with host buffers (camera H2D + result D2H inside the timed region)
+    # ---- e2e: the same metric through the C ABI with HOST buffers: camera H2D + the step's result D2H inside the timed region
     cam_host = np.array(cam)
     out_kind = "frame" if shadows else "albedo"
-    full_pinned = ctx.pinned_empty(W * H * 4, np.uint32) if (tiled and rank == 0) else None
-    pinned2 = [pinned, ctx.pinned_empty(pinned.nbytes, np.uint32)]  # double-buffered host target of the pipelined readback
+    host_frame = shm = None
+    if tiled:
+        # every rank copies ITS bands straight into one shared, page-locked host frame: N PCIe links in parallel
+        name = D.bcast("uvt_frame_%d_%s" % (os.getpid(), workload) if rank == 0 else None)
+        if rank == 0:
+            shm = uvt.tiles.SharedHostFrame(name, W, H, create=True)
+        D.barrier()
+        if rank != 0:
+            shm = uvt.tiles.SharedHostFrame(name, W, H, create=False)
+        host_frame = shm.array
+        ctx.host_register(host_frame)
+        ctx.bind_frame_target(0, global_rows=False)   # bands stay in this rank's own frame buffer
+    else:
+        pinned2 = [ctx.pinned_empty(W * H * 4, np.uint32), ctx.pinned_empty(W * H * 4, np.uint32)]
 
     def e2e_step(i):
         ctx.set_camera(my_poses[i % len(my_poses)] if sweep else cam_host)
         (ctx.dispatch_frame if shadows else ctx.dispatch_primary)()
-        if not tiled:
-            # pipelined D2H into pinned host memory: frame i lands while frame i+1 renders (uvt_readback_async)
-            ctx.readback_async(out_kind, pinned2[i & 1])
-            return
-        # tiled frame: the step's result is the assembled frame on the presenting rank
-        if p2p:
-            ctx.sync()
-            if use_dist:
-                dist.barrier()
-            if rank == 0:
-                ctx.read_device(shared_ptr, full_pinned)
+        if tiled:
+            ctx.readback_bands_async(host_frame)
         else:
-            gather_step()
-            if rank == 0:
-                ctx.read_device(full_frame.data_ptr(), full_pinned)
+            ctx.readback_async(out_kind, pinned2[i & 1])  # frame i lands while frame i+1 renders
 
     for i in range(2):
         e2e_step(i)
     ctx.readback_wait()
-    barrier()
+    D.barrier()
     e0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         e2e_step(i)
     ctx.readback_wait()  # every frame of the timed region has landed in host memory
-    barrier()
+    D.barrier()
     e2e_s = time.perf_counter() - e0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if use_dist:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = rays_all * args.steps / float(te.item()) / 1e9
-    d2h_bytes = W * H * 4 if tiled else int(pinned.nbytes)
+    e2e_s = D.reduce([e2e_s], "max")[0]
+    e2e_value = rays_all * steps / e2e_s / 1e9
+    d2h_local = W * ctx.local_rows() * 4
+    e2e_ok = None
+    if tiled:
+        # the frame assembled in host memory by the N copies equals the frame assembled on rank 0's GPU
+        D.barrier()
+        if rank == 0 and p2p:
+            e2e_ok = bool(np.array_equal(host_frame, host_p2p))
+    d2h_rates = D.gather_obj(round(d2h_local * steps / e2e_s / 1e9, 2))
+    all_clocks = D.gather_obj(clocks)
 
+    rec = None
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        kms = float(np.mean(kernel_ms))
-        achieved = alg_step / (kms * 1e-3) / 1e9
+        kms = float(np.mean(primary_ms))
+        achieved = alg_primary / (kms * 1e-3) / 1e9
         l2_gbps = ctx.measure_l2_read_gbps(32 << 20, 50)
-        line = {
-            "metric": "rays_per_second", "value": value, "unit": "Grays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if tiled else "weak", "vs_baseline": None,
+        sm = [c["sm_mhz"] for c in all_clocks if c.get("sm_mhz")]
+        reasons = sorted({r for c in all_clocks for r in c.get("reasons", [])})
+        rec = {
+            "metric": "rays_per_second", "value": value, "unit": "Grays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong" if tiled else "weak", "vs_baseline": None,
             "dtype": "f32+i32", "data": "synthetic (procgen world, reference seeds; 29 block models from the reference .vox set)",
             "config": {"workload": desc, "rays_per_step_all_ranks": rays_all, "layout": ctx.effective_layout(), "scheduler": args.scheduler, "dense_grid": not args.no_dense,
-                       "parallelism": ("interleaved %d-row bands over %d ranks + NCCL gather" % (band, world)) if tiled else
-                                      ("poses sharded over %d ranks" % world if sweep else "one independent frame per rank per step, world replicated, no collective"),
+                       "parallelism": ("one %dx%d frame in interleaved %d-row bands over %d ranks, world replicated" % (W, H, band, world)) if tiled else
+                                      ("poses sharded over %d ranks" % world if sweep else
+                                       ("one independent frame per rank per step, world replicated, no collective" if world > 1 else "single GPU")),
                        "l2": "not flushed" if args.no_flush else "flushed between timed steps by a 256 MiB fill (untimed)",
-                       "timing": "CUDA events on the launch stream per step, summed; max over ranks", "world_build_s": round(build_s, 2)},
-            "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": 96, "d2h_bytes_per_step": d2h_bytes,
-                    "what": ("uvt_set_camera + dispatch + (band exchange) + D2H of the assembled RGBA8 frame on rank 0 into pinned host memory, wall clock" if tiled
-                             else "per step: uvt_set_camera + dispatch + uvt_readback_async of the RGBA8 %s into pinned host memory (frame i is copied out while frame i+1 renders; all frames landed before the clock stops), wall clock" % out_kind)},
+                       "timing": "CUDA events on the launch stream per step; per step the max over ranks, summed over the steps", "world_build_s": round(build_s, 2)},
+            "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": 96 * world, "d2h_bytes_per_step": W * H * 4 if tiled else d2h_local * world,
+                    "ms_per_step": e2e_s / steps * 1e3, "d2h_gb_per_s_per_rank": d2h_rates,
+                    "what": ("per step and rank: uvt_set_camera + dispatch + uvt_readback_bands_async of the rank's RGBA8 bands into ONE shared page-locked host frame "
+                             "(N device-to-host copies in parallel, no GPU-to-GPU hop); all frames landed before the clock stops; wall clock, max over ranks" if tiled else
+                             "per step: uvt_set_camera + dispatch + uvt_readback_async of the RGBA8 %s (4 B/px; the 24 B/px G-buffer and the 28 B/px hit buffer stay on the device) into pinned host "
+                             "memory, frame i copied out while frame i+1 renders; all frames landed before the clock stops; wall clock" % out_kind)},
             "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel_ms": kms,
-                         "algorithmic_bytes_per_launch": alg_step,
+            "clocks": {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max([c.get("sm_max_mhz") or 0 for c in all_clocks]) or None,
+                       "reasons": reasons, "samples": int(sum(c.get("samples", 0) for c in all_clocks)),
+                       "per_rank_sm_mhz": [c.get("sm_mhz") for c in all_clocks]},
+            "roofline": {"bound": "l2", "kernel": "primary_kernel (the dominant launch of the step)", "achieved": achieved, "peak": l2_gbps, "unit": "GB/s",
+                         "frac": achieved / l2_gbps, "traffic": ncu_traffic(workload),
+                         "peak_source": "L2 read bandwidth measured in this run (16-B ld.global.cg over a 32 MiB resident buffer); MEASURED_PEAKS.json has no L2 figure",
+                         "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_primary,
+                         "hbm_frac": achieved / peaks["hbm_gbs"], "hbm_peak": peaks["hbm_gbs"], "hbm_peak_source": peak_src,
                          "primary_trips": cp["t_in"], "primary_trips_with_fetch": fetch["lookups"] if fetch else cp["t_in"],
-                         "note": "algorithmic bytes = reference access pattern (4*T_in+4*T_chunk+4*T_block+G-buffer), exact counters; "
-                                 "the traversal data is cache resident, so the binding roofline is L2 (roofline_l2)"},
-            "roofline_l2": {"bound": "l2", "achieved": achieved, "peak": l2_gbps, "unit": "GB/s", "frac": achieved / l2_gbps,
-                            "peak_source": "measured in this run: 16-B ld.global.cg reads of a 32 MiB L2-resident buffer"},
-            "wall_ms_per_step": wall / args.steps * 1e3,
+                         "note": "algorithmic bytes = reference access pattern of this rank's primary pass (4*T_in + 4*T_chunk + 4*T_block + 24 B/px), exact counters; "
+                                 "the kernel itself is bound by instruction issue (profiles/), the traversal data is cache resident"},
+            "wall_ms_per_step": wall / steps * 1e3,
         }
         if pass_ms:
-            line["pass_ms"] = pass_ms
+            rec["pass_ms"] = pass_ms
         if tiled:
-            line["gather_ms"] = float(np.mean(gather_ms)) if gather_ms else 0.0
-            line["config"]["gather"] = ("p2p: kernels store bands into rank 0's frame over NVLink (CUDA IPC peer mapping), no collective"
-                                        if p2p else "nccl: torch.distributed.gather of band buffers + reassembly kernel")
+            rec["config"]["exchange"] = ("p2p: every rank's shade kernel stores its finished bands into rank 0's frame over NVLink (CUDA IPC peer mapping), inside the timed region"
+                                         if p2p else "nccl: band buffers gathered to rank 0 (NCCL) + reassembly kernel, inside the timed region")
             if verified is not None:
-                line["config"]["p2p_frame_equals_nccl_gather"] = verified
-        if args.gpus == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(uvt, args, dim, W, H, shadows, cam)
-        print(json.dumps(line))
+                rec["config"]["p2p_frame_equals_nccl_gather"] = verified
+            if e2e_ok is not None:
+                rec["e2e"]["host_frame_equals_device_frame"] = e2e_ok
+        if want_cpu_baseline:
+            rec["cpu_baseline"] = cpu_baseline(uvt, bm, dim, W, H, shadows, cam, models)
+
+    if tiled:
+        ctx.readback_wait()
+        ctx.host_unregister(host_frame)
+        host_frame = None
+        D.barrier()
+        shm.close()
     if p2p and rank != 0:
         ctx.bind_frame_target(0, global_rows=False)
         ctx.shared_frame_close(shared_ptr)
-    if use_dist:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.barrier()
+    ctx.close()
+    del flush, gather_buf, full_frame
+    torch.cuda.empty_cache()
+    return rec
 
 
-def cpu_baseline(uvt, args, dim, W, H, shadows, cam):
+def run_ours(args):
+    import torch
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    D = Dist(torch, rank, local_rank, world)
+    uvt = importlib.import_module("unnamed-voxel-tracer_b200")
+    models = load_models()
+    line = measure(uvt, torch, D, args, args.workload, args.steps, args.warmup, models, None,
+                   want_cpu_baseline=(args.gpus == 1 and not args.no_cpu_baseline))
+    if not args.no_also and args.workload == "c3":
+        also = {}
+        for wl, st in (("c4", max(30, min(args.steps, 60))), ("c2", args.steps)):
+            r = measure(uvt, torch, D, args, wl, st, args.warmup, models, None, want_cpu_baseline=False)
+            if r:
+                also[wl] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "e2e", "roofline", "gpu_launches") if k in r}
+                also[wl]["workload"] = r["config"]["workload"]
+                also[wl]["parallelism"] = r["config"]["parallelism"]
+                if "pass_ms" in r:
+                    also[wl]["pass_ms"] = r["pass_ms"]
+                for k in ("exchange", "p2p_frame_equals_nccl_gather"):
+                    if k in r["config"]:
+                        also[wl][k] = r["config"][k]
+        if line:
+            line["also"] = also
+    if line:
+        print(json.dumps(line))
+    D.close()
+
+
+def cpu_baseline(uvt, bm, dim, W, H, shadows, cam, models):
     """The oracle (CPU port of the reference GLSL) on this box's host cores: bounded sample of the same workload."""
     import oracle
     oracle.set_num_threads(os.cpu_count() or 1)
     scale = 1 if W * H <= 1920 * 1080 and dim <= 512 else 4
     Ws, Hs = W // scale, H // scale
-    bm = uvt.voxel.VoxelBrickmap.init(dim)
-    uvt.procgen.procgen(dim, bm)
-    ow = oracle.World(dim, bm.chunks(), bm.bricks(), oracle.atlas_from_models(load_models()))
+    ow = oracle.World(dim, bm.chunks(), bm.bricks(), oracle.atlas_from_models(models))
     prm = oracle.params(dim)
     best, rays = None, 0
     for _ in range(3):
@@ -464,7 +541,8 @@ def cpu_baseline(uvt, args, dim, W, H, shadows, cam):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return {"value": rays / best / 1e9, "unit": "Grays/s", "cores": oracle.num_threads(), "kind": "port",
-            "sample": f"{Ws}x{Hs} frame of the same workload, best of 3, OpenMP over rows", "ms_per_frame_sample": best * 1e3}
+            "sample": f"{Ws}x{Hs} frame of the same workload ({'full size' if scale == 1 else '1/%d of the pixels' % (scale * scale)}), best of 3, OpenMP over rows",
+            "ms_per_frame_sample": best * 1e3}
 
 
 if __name__ == "__main__":

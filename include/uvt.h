@@ -212,6 +212,13 @@ size_t uvt_buffer_bytes(uvt_ctx *ctx, uvt_buffer_kind kind);
  * a third call first waits for the oldest.  uvt_readback_wait() returns when every outstanding copy has landed. */
 int  uvt_readback_async(uvt_ctx *ctx, uvt_buffer_kind kind, void *dst, size_t bytes);
 int  uvt_readback_wait(uvt_ctx *ctx);
+/* Tiled frames end to end: copy this ctx's FRAME bands to where they belong in a full W x H RGBA8 host
+ * frame.  Every rank calls it on the same host frame (shared memory, page-locked with uvt_host_register in each
+ * process): the frame is assembled in host memory by N parallel device-to-host copies, one per PCIe link, instead of
+ * being gathered onto one GPU first.  Pipelined like uvt_readback_async; uvt_readback_wait() waits for it. */
+int  uvt_readback_bands_async(uvt_ctx *ctx, void *host_frame, size_t frame_bytes);
+int  uvt_host_register(uvt_ctx *ctx, void *p, size_t bytes);
+int  uvt_host_unregister(uvt_ctx *ctx, void *p);
 /* Device address of a buffer (for NCCL / peer access by the caller's communication layer). */
 int  uvt_device_ptr(uvt_ctx *ctx, uvt_buffer_kind kind, void **dptr);
 /* Redirect the FRAME output to caller-owned device memory (may be a peer-mapped

@@ -286,6 +286,35 @@ def test_partition_union_equals_full_frame(uvt, oracle, w1):
     assert np.array_equal(pos.view(np.uint32), full["position"].view(np.uint32))
 
 
+def test_band_readback_assembles_the_frame_in_host_memory(uvt, oracle, w1):
+    """uvt_readback_bands_async: every part copies its bands straight to their rows of ONE host frame (the e2e path of a
+    tiled frame: N parallel device-to-host copies, no GPU-to-GPU hop) — ragged last band included."""
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    W, H = 320, 200  # 13 bands of 16 rows, the last one 8 rows
+    cam = camera_k1(uvt, oracle)
+    ctx.set_partition(8, 1, 0)
+    ctx.resize(W, H)
+    full = gpu_render(ctx, cam)["frame"]
+    shm = uvt.tiles.SharedHostFrame("uvt_test_frame_%d" % __import__("os").getpid(), W, H, create=True)
+    try:
+        shm.array[:] = 0
+        ctx.host_register(shm.array)
+        for n_parts in (1, 3, 4):
+            shm.array[:] = 0xDEADBEEF
+            for part in range(n_parts):
+                ctx.set_partition(16, n_parts, part)
+                ctx.set_camera(cam)
+                ctx.dispatch_frame()
+                ctx.readback_bands_async(shm.array)
+            ctx.readback_wait()
+            assert np.array_equal(shm.array, full), n_parts
+        ctx.host_unregister(shm.array)
+    finally:
+        ctx.set_partition(8, 1, 0)
+        shm.close()
+
+
 def test_batched_poses_equal_single_dispatches(uvt, oracle, w1):
     ctx, sc = w1
     ctx.resize(160, 90)

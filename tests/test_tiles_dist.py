@@ -102,3 +102,22 @@ def test_sweep_poses_are_reproducible_and_inside(uvt):
     assert (pos[:, [0, 2]] > 25).all() and (pos[:, [0, 2]] < 487).all() and (pos[:, 1] >= 19).all()
     m = a["cam_mat"].reshape(-1, 4, 4)
     assert np.allclose(np.einsum("nij,nkj->nik", m, m), np.eye(4), atol=1e-5)  # rotations
+
+
+def test_shared_host_frame_is_one_mapping(uvt):
+    """The e2e target of a tiled frame: one POSIX shared-memory frame, every rank writes its own bands."""
+    import os
+    W, H, band, n = 64, 40, 8, 3
+    name = "uvt_cpu_test_%d" % os.getpid()
+    a = uvt.tiles.SharedHostFrame(name, W, H, create=True)
+    b = uvt.tiles.SharedHostFrame(name, W, H, create=False)
+    try:
+        a.array[:] = 0
+        for part in range(n):
+            g = uvt.tiles.local_to_global_rows(H, band, n, part)
+            b.array[g[g >= 0]] = part + 1
+        want = (np.arange(H) // band) % n + 1
+        assert np.array_equal(a.array[:, 0], want) and np.array_equal(a.array[:, -1], want)
+    finally:
+        b.close()
+        a.close()

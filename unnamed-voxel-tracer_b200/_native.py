@@ -87,6 +87,9 @@ SIGNATURES = {
     "uvt_buffer_bytes": (c_size, [c_p, c_int]),
     "uvt_readback_async": (c_int, [c_p, c_int, c_p, c_size]),
     "uvt_readback_wait": (c_int, [c_p]),
+    "uvt_readback_bands_async": (c_int, [c_p, c_p, c_size]),
+    "uvt_host_register": (c_int, [c_p, c_p, c_size]),
+    "uvt_host_unregister": (c_int, [c_p, c_p]),
     "uvt_device_ptr": (c_int, [c_p, c_int, P(c_p)]),
     "uvt_bind_frame_target": (c_int, [c_p, c_p, c_u32, c_u32]),
     "uvt_deinterleave": (c_int, [c_p, c_p, c_p, c_u32]),

@@ -625,16 +625,17 @@ __global__ void quad_clear_kernel(const unsigned int *__restrict__ tops32, uint1
     clear4[i] = (uint16_t)m;
 }
 
-// clear64[Q] = max of clear4 over the 16x16 groups of the 64x64-block column group Q (the last one may be partial)
-__global__ void coarse_clear_kernel(const uint16_t *__restrict__ clear4, uint16_t *__restrict__ clear64, int dim) {
-    const int qdim = dim >> 2, cdim = (dim + 63) >> 6;
+// Next level of the column-tops pyramid: out[Q] = max of `in` over the 4x4 cells of group Q (the last groups may be partial).
+// clear4 (4x4 blocks, grown by one block) -> clear16 -> clear64: line_free_trips walks the coarsest level first.
+__global__ void coarse_clear_kernel(const uint16_t *__restrict__ in, uint16_t *__restrict__ out, int in_dim) {
+    const int out_dim = (in_dim + 3) >> 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cdim * cdim) return;
-    const int cx = i % cdim, cz = i / cdim;
+    if (i >= out_dim * out_dim) return;
+    const int cx = i % out_dim, cz = i / out_dim;
     unsigned int m = 0;
-    for (int z = 16 * cz; z < min(16 * cz + 16, qdim); ++z)
-        for (int x = 16 * cx; x < min(16 * cx + 16, qdim); ++x) m = max(m, (unsigned int)clear4[x + qdim * z]);
-    clear64[i] = (uint16_t)m;
+    for (int z = 4 * cz; z < min(4 * cz + 4, in_dim); ++z)
+        for (int x = 4 * cx; x < min(4 * cx + 4, in_dim); ++x) m = max(m, (unsigned int)in[x + in_dim * z]);
+    out[i] = (uint16_t)m;
 }
 
 // Block-level clearance.  One CTA per brick, one thread per block.  The occupancy of the 5x5x5 chunk

@@ -88,7 +88,8 @@ struct WorldCompact {
     int32_t dim;                            // MAP_DIMENSION in blocks
     const uint8_t *__restrict__ dense;      // [dim^3] one byte per block, x + dim*(z + dim*y): the brick bytes (far-empty chunks:
                                             // kMatLimit + min(n_free, 30)) without the chunk indirection; nullptr when not built
-    const uint16_t *__restrict__ clear64;   // [ceil(dim/64)^2] maximum of clear4 over 64x64-block column groups (coarse sky_sealed walk)
+    const uint16_t *__restrict__ clear64;   // [ceil(dim/64)^2] maximum of clear4 over 64x64-block column groups (coarsest level of the walk)
+    const uint16_t *__restrict__ clear16;   // [ceil(dim/16)^2] ... over 16x16-block column groups
     const uint16_t *__restrict__ clear4;    // [(dim/4)^2] per 4x4-block column group, grown by one block on every side:
                                             // every block with y >= clear4 there is empty (sky_sealed)
 
@@ -274,6 +275,75 @@ __device__ __noinline__ bool sky_sealed(const uint16_t *__restrict__ clear4, con
     return sky_walk<4>(clear4, dim >> 2, y_all, px, py, pz, dx, dy, dz, inv_dx, inv_dz, t_stop);
 }
 
+// ---- free trips from the column tops: "how long does this ray stay in open air?" ---------------------
+// Generalises sky_sealed() to rays of ANY direction and to a trip COUNT instead of a yes/no: returns n, the number of
+// FOLLOWING trips (after the current one, whose lookup found an empty block) that provably stay inside the map and look
+// up empty blocks; n == n_rem means the ray is sealed (iteration-cap miss, map.glsl:167).
+//
+// Why the column tops decide this.  While every lookup is empty the ray stays at block steps, and its state S = g + within
+// moves along straight pieces parallel to dir: `within += dir * t[minIdx]` advances all three axes by the same parameter,
+// and the stepped axis is put exactly on the block face it reached (travelling up an axis) or 0.001 block past it
+// (travelling down: the 0.999 reset, map.glsl:162).  So after any number of trips S = P + dir * tau + J with P the
+// state now, tau >= 0 and J_k in [-0.001 * trips, 0] on the axes travelled downwards, 0 on the others.  A lookup names
+// block floor(S) or, per axis, the next one up when `within` has rounded up to the step size (the carry of
+// trace_map_fast's free-trip bound).  Hence, for the line point L = P + dir * tau:
+//   * the looked-up COLUMN is within one block of L's column: clear4 / clear64 hold the tops of column groups grown by
+//     one block sideways, so the group that contains L covers it;
+//   * the looked-up ROW is >= floor(L.y - 0.001 * trips): it is empty when L.y - margin >= top of that group, with
+//     margin = 0.001 * trips + slack for the fp32 arithmetic of THIS test (positions < 4096 blocks: errors < 0.003);
+//   * g stays inside the map while L stays one block away from the three map faces ahead (t_face below).
+// A trip crosses one block face, so after j trips |S - P|_1 < j + 3 blocks and tau < (j + 3.6) / |dir|_1: trips
+// j < t_safe * |dir|_1 - 3.6 look up blocks the walk has covered, where [0, t_safe) is the parameter range proven
+// clear.  The walk is a 2-D DDA over the 64x64-block groups first (a handful of cells for the whole reach) and continues
+// over the 4x4-block groups from where the coarse level stopped.  It decides only WHETHER fetches can be skipped — the
+// ray's own arithmetic is untouched — so it needs no bit-exact arithmetic (fused multiply-adds are fine here).
+template <int CELL>
+__device__ __forceinline__ float tops_walk(const uint16_t *__restrict__ tops, int qdim, float y_all, float margin, float t0, float t_end,
+                                           float px, float py, float pz, float dx, float dy, float dz, float invx, float invz, int max_iter) {
+    const float x0 = __fmaf_rn(dx, t0, px), z0 = __fmaf_rn(dz, t0, pz);
+    int qx = (int)(x0 * (1.0f / CELL)), qz = (int)(z0 * (1.0f / CELL));
+    const bool up = dy > 0.0f;
+    const int sx = dx > 0.0f ? 1 : -1, sz = dz > 0.0f ? 1 : -1;
+    float tmx = ((float)((qx + (dx > 0.0f ? 1 : 0)) * CELL) - px) * invx;  // line parameter at the next x / z group boundary
+    float tmz = ((float)((qz + (dz > 0.0f ? 1 : 0)) * CELL) - pz) * invz;
+    const float tdx = (float)CELL * fabsf(invx), tdz = (float)CELL * fabsf(invz);
+    float t = t0;
+    for (int it = 0; it < max_iter; ++it) {
+        if ((unsigned)qx >= (unsigned)qdim || (unsigned)qz >= (unsigned)qdim) break;  // (t < t_face keeps the line inside: insurance)
+        const float t_out = fminf(fminf(tmx, tmz), t_end);
+        const float y_lo = __fmaf_rn(dy, up ? t : t_out, py) - margin;  // lowest point of the line inside this group
+        if (y_lo < (float)__ldg(&tops[qx + qdim * qz])) break;
+        if (up && y_lo >= y_all) return t_end;  // climbing above every occupied block of the world
+        t = t_out;
+        if (t >= t_end) break;
+        if (tmx < tmz) { tmx += tdx; qx += sx; }
+        else { tmz += tdz; qz += sz; }
+    }
+    return t;
+}
+
+__device__ __noinline__ int line_free_trips(const uint16_t *__restrict__ clear4, const uint16_t *__restrict__ clear16,
+                                            const uint16_t *__restrict__ clear64, int dim, int y_clear,
+                                            float px, float py, float pz, float dx, float dy, float dz, float invx, float invy, float invz,
+                                            int n_rem) {
+    const float l1 = fabsf(dx) + fabsf(dy) + fabsf(dz);
+    const float t_want = (float)(n_rem + 5) / l1;
+    // the line stays one block away from the map faces ahead for parameters below t_face
+    const float hi = (float)(dim - 1);
+    const float ax = (dx > 0.0f ? hi - px : px - 1.0f) * fabsf(invx);
+    const float ay = (dy > 0.0f ? hi - py : py - 1.0f) * fabsf(invy);
+    const float az = (dz > 0.0f ? hi - pz : pz - 1.0f) * fabsf(invz);
+    const float t_end = fminf(t_want, fminf(fminf(ax, ay), az));
+    if (!(t_end > 0.0f)) return 0;
+    const float margin = 0.0625f + 0.001f * (float)(n_rem + 1);
+    const float y_all = (float)y_clear;
+    float t_safe = tops_walk<64>(clear64, (dim + 63) >> 6, y_all, margin, 0.0f, t_end, px, py, pz, dx, dy, dz, invx, invz, 12);
+    if (t_safe < t_end) t_safe = tops_walk<16>(clear16, (dim + 15) >> 4, y_all, margin, t_safe, t_end, px, py, pz, dx, dy, dz, invx, invz, 32);
+    if (t_safe < t_end) t_safe = tops_walk<4>(clear4, dim >> 2, y_all, margin, t_safe, t_end, px, py, pz, dx, dy, dz, invx, invz, 64);
+    const int n = (int)(t_safe * l1 - 4.5f);
+    return min(max(n, 0), n_rem);
+}
+
 // One DDA step (map.glsl:157-162), hand-scheduled and branch-free: 6 ops for t, 3 compares, min3,
 // 6 ops for within += dir * t[minIdx], then the stepped axis is reset / advanced under its predicate.
 // .rn ops are never contracted.  t[minIdx] is the minimum of the three (ties carry equal values;
@@ -394,6 +464,15 @@ __device__ __forceinline__ void dda_step_last(int &gx, int &gy, int &gz, float &
 // Rays with non-finite reciprocals or origins beyond 2^20 sub-voxels take the generic path,
 // whose corner-case behaviour (NaN ordering, saturation) is the specification.
 constexpr int kDead = 0x40000000;    // `limit` of a lane without a live ray
+#ifndef UVT_WALK_GAP
+#define UVT_WALK_GAP 8
+#endif
+#ifndef UVT_WALK_BACKOFF_SHIFT
+#define UVT_WALK_BACKOFF_SHIFT 3
+#endif
+constexpr int kWalkUseful = 4;                  // a walk that proves fewer free trips than this counts as failed
+constexpr int kWalkGap = UVT_WALK_GAP;          // trips between the end of a proven run and the lane's next walk
+constexpr int kWalkBackoffShift = UVT_WALK_BACKOFF_SHIFT;  // ... after a failed walk: max_steps >> this (24 of 192 trips, 6 of 48)
 
 // Must be called by ALL 32 lanes of a warp (it uses full-mask warp reductions); `active` = this lane has a ray.
 template <int COUNT, bool DENSE>
@@ -435,20 +514,13 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
         if (COUNT) tc.t_in = tc.t_chunk = tc.t_block = 0;
     }
 
-    // no map face in the direction of travel within reach of the remaining trips (one block per trip)
-    const int reach = max_steps + 2;
-    const bool no_exit = (posx ? w.dim - 1 - (gx >> 3) : (gx >> 3)) >= reach && (posy ? w.dim - 1 - (gy >> 3) : (gy >> 3)) >= reach &&
-                         (posz ? w.dim - 1 - (gz >> 3) : (gz >> 3)) >= reach;
-    const bool climbs = COUNT != 1 && posy && no_exit;
-
     const uint32_t cd1 = w.cd1;
     int trip = 0;                     // warp-uniform
     int limit = fast ? 0 : kDead;     // trips in [trip, limit) need no lookup; kDead parks the lane
     bool mx = true, my = false;       // minIdx of the previous trip == 0 / == 1 (starts at 0, map.glsl:98)
-    // warp-uniform: DDA runs stop at the segment ends 4, 32, 64, 128, ... (4, 12, 28 for the 48-trip shadow cap), where the
-    // climbing lanes try sky_sealed() together.  Measured on the default world, 63 % of the sky rays pass at trip 4 and most
-    // of the rest at 32 / 64 / 128; a failed test is cheap.
-    int seg_end = min(4, max_steps);
+    // the lane may run the column-tops walk (line_free_trips) from this trip on: at once, then again some trips after the
+    // run it proved has been used up (kWalkGap), later after a walk that proved next to nothing (kWalkBackoff)
+    int walk_at = COUNT == 1 ? kDead : 0;
 
     uint32_t cmat = 0;  // material of the block looked up last (0: none) — sub-voxel steps mostly stay inside it
 
@@ -458,6 +530,7 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
         // free trips ran out: a lane still inside its free run re-reads an (empty) block and refreshes
         // its clearance from the new position, which keeps the lanes' lookups aligned (fewer rounds).
         bool slow = limit < kDead;
+        bool walk = false;  // this round's lookup found an empty block and the lane is due for a column-tops walk
         if (DENSE && COUNT != 1 && slow) {
             // the common lookup, kept short: a block step (no round-up carry) inside the map that finds an empty block and
             // does not seal the ray.  Anything else falls through to the general code below, which redoes the lookup.
@@ -468,10 +541,10 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
             if (inside) code = __ldg(&w.dense[(size_t)((uint32_t)gx >> 3) + (size_t)udim * (((uint32_t)gz >> 3) + udim * ((uint32_t)gy >> 3))]);
             const int lim0 = max(limit, trip + 1 + (int)code - (int)kMatLimit);
             const bool simple = big && code >= kMatLimit && fmaxf(fmaxf(wx, wy), wz) < 8.0f;
-            const bool seals = lim0 >= max_steps || (climbs && (gy >> 3) >= w.y_clear);
-            if (simple && !seals) {
+            if (simple && lim0 < max_steps) {  // (a run that reaches the cap seals the ray: general code)
                 limit = lim0;
                 slow = false;
+                walk = trip >= walk_at;
 #ifndef UVT_ROUND_STATS
                 if (COUNT == 2) tc.t_in++;
 #endif
@@ -537,8 +610,9 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
                 out.px = px; out.py = py; out.pz = pz;
                 if (COUNT == 1) n_free = 0;  // exact reference counters need every lookup
                 limit = max(limit, trip + 1 + n_free);  // an earlier guarantee stays valid
-                const bool seal = COUNT != 1 && mat == 0u && (limit >= max_steps || (climbs && (gy >> 3) >= w.y_clear));
+                const bool seal = COUNT != 1 && mat == 0u && limit >= max_steps;
                 limit = min(limit, max_steps);
+                walk = mat == 0u && !seal && trip >= walk_at;
                 if (seal) {
                     // sealed: nothing but empty in-map blocks until the iteration cap (map.glsl:167)
                     out.trips = (uint32_t)max_steps;
@@ -585,9 +659,24 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
             }
         }
 
+        // ---- column-tops walk: many free trips at once, or the seal (sealed rays, above) ----------
+        if (COUNT != 1 && walk) {
+            const int n_rem = max_steps - trip - 1;
+            const int n = line_free_trips(w.clear4, w.clear16, w.clear64, w.dim, w.y_clear, ((float)gx + wx) * 0.125f, ((float)gy + wy) * 0.125f,
+                                          ((float)gz + wz) * 0.125f, dx, dy, dz, invx, invy, invz, n_rem);
+            if (n >= n_rem) {  // nothing but empty in-map blocks until the iteration cap (map.glsl:167)
+                out.trips = (uint32_t)max_steps;
+                out.px = out.py = out.pz = 0xFFFFFFFFu;
+                limit = kDead;
+            } else {
+                limit = max(limit, trip + 1 + n);
+                walk_at = trip + 1 + n + (n < kWalkUseful ? max_steps >> kWalkBackoffShift : kWalkGap);
+            }
+        }
+
         // ---- how many trips can the whole warp run without a lookup? ----------------------
-        // live lanes: 1 <= limit - trip (limit is clamped to max_steps > trip); parked lanes: huge
-        int k = __reduce_min_sync(0xFFFFFFFFu, limit - trip);
+        // live lanes: 1 <= limit - trip <= max_steps - trip; parked lanes: huge
+        const int k = __reduce_min_sync(0xFFFFFFFFu, limit - trip);
         if (k >= kDead / 2) break;  // no live lane left
 #ifdef UVT_ROUND_STATS
         if (COUNT == 2) {  // experiment build: t_in = rounds, t_chunk = single-trip rounds forced by a sub-voxel lane, t_block = by a block-step lane
@@ -600,7 +689,6 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
             }
         }
 #endif
-        k = min(k, seg_end - trip);  // warp-uniform; >= 1
 
         // ---- k DDA steps, branch-free (map.glsl:157-162) -----------------------------------
         for (int j = 1; j < k; ++j) dda_step(gx, gy, gz, wx, wy, wz, isx, isy, isz, tgx, tgy, tgz, invx, invy, invz, dx, dy, dz, rsx, rsy, rsz);
@@ -611,22 +699,12 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
             my = myi != 0;
         }
         trip += k;
-        if (trip == seg_end) {  // warp-uniform
-            if (trip >= max_steps) {  // iteration cap: miss (map.glsl:167); in lockstep it ends every live lane at once
-                if (limit < kDead) {
-                    out.trips = (uint32_t)trip;
-                    out.px = out.py = out.pz = 0xFFFFFFFFu;
-                }
-                break;
-            }
-            seg_end = min(max_steps > 64 ? (seg_end == 4 ? 32 : 2 * seg_end) : 2 * seg_end + 4, max_steps);
-            // ---- sealed-ray test (c), all candidate lanes of the warp at once ----------------
-            if (climbs && limit < kDead && big &&
-                sky_sealed(w.clear4, w.clear64, w.dim, w.y_clear, ((float)gx + wx) * 0.125f, ((float)gy + wy) * 0.125f, ((float)gz + wz) * 0.125f, dx, dy, dz, max_steps - trip)) {
-                out.trips = (uint32_t)max_steps;  // iteration-cap miss (map.glsl:167)
+        if (trip >= max_steps) {  // iteration cap: miss (map.glsl:167); in lockstep it ends every live lane at once
+            if (limit < kDead) {
+                out.trips = (uint32_t)trip;
                 out.px = out.py = out.pz = 0xFFFFFFFFu;
-                limit = kDead;
             }
+            break;
         }
     }
     if (COUNT == 1 && fast) tc.t_in = out.trips;  // every executed trip passed the bounds test

@@ -62,7 +62,8 @@ struct uvt_ctx {
     bool incremental_ok = false;        // the last full commit left everything uvt_world_commit_region needs
     int32_t y_clear = 0;            // max occupied block y + 1 (every block at or above is empty)
     uint16_t *d_clear4 = nullptr;   // [(dim/4)^2] dilated column-group tops for sky_sealed()
-    uint16_t *d_clear64 = nullptr;  // [ceil(dim/64)^2] their maxima over 64x64-block groups
+    uint16_t *d_clear16 = nullptr;  // [ceil(dim/16)^2] their maxima over 16x16-block groups
+    uint16_t *d_clear64 = nullptr;  // [ceil(dim/64)^2] ... over 64x64-block groups
     uint8_t *d_dense = nullptr;     // [dim^3] dense block grid (nullptr: not built — too large or disabled)
     bool dense_valid = false;
     bool world_committed = false;
@@ -276,6 +277,7 @@ WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     a.w.y_clear = c->y_clear;
     a.w.dim = (int32_t)c->dim;
     a.w.clear4 = c->d_clear4;
+    a.w.clear16 = c->d_clear16;
     a.w.clear64 = c->d_clear64;
     a.w.dense = c->d_dense;
     a.w.bricks8 = c->d_bricks8;
@@ -443,9 +445,10 @@ int upload_material_lut(uvt_ctx *c, uint32_t *d_keys, uint8_t *d_vals) {
 int finish_tops(uvt_ctx *c, unsigned int *d_max) {
     const int nq = (int)((c->dim / 4) * (c->dim / 4));
     quad_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_tops32, c->d_clear4, (int)c->dim);
-    const int nc = (int)(((c->dim + 63) / 64) * ((c->dim + 63) / 64));
-    coarse_clear_kernel<<<(nc + 127) / 128, 128, 0, c->stream>>>(c->d_clear4, c->d_clear64, (int)c->dim);
-    c->launches++;
+    const int d4 = (int)(c->dim / 4), d16 = (d4 + 3) / 4, d64 = (d16 + 3) / 4;
+    coarse_clear_kernel<<<(d16 * d16 + 127) / 128, 128, 0, c->stream>>>(c->d_clear4, c->d_clear16, d4);
+    coarse_clear_kernel<<<(d64 * d64 + 127) / 128, 128, 0, c->stream>>>(c->d_clear16, c->d_clear64, d16);
+    c->launches += 2;
     UVT_CUDA(c, cudaMemsetAsync(d_max, 0, 4, c->stream));
     max_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, nq, d_max);
     c->launches += 2;
@@ -657,7 +660,7 @@ void uvt_destroy(uvt_ctx *c) {
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
     cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
     cudaFree(c->d_rowmask); cudaFree(c->d_brick_chunk); cudaFree(c->d_tops32); cudaFree(c->d_scratch);
-    cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]); cudaFree(c->d_clear64);
+    cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]); cudaFree(c->d_clear64); cudaFree(c->d_clear16);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
     cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame);
     for (int i = 0; i < 4; ++i)
@@ -755,8 +758,8 @@ int uvt_pipeline_dispatch(uvt_pipeline *p, uint32_t gx, uint32_t gy, uint32_t gz
 static int reset_world(uvt_ctx *c, uint32_t dim) {
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
-    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32); cudaFree(c->d_clear64);
-    c->d_clear64 = nullptr;
+    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32); cudaFree(c->d_clear64); cudaFree(c->d_clear16);
+    c->d_clear64 = c->d_clear16 = nullptr;
     cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]);
     c->d_field = c->d_field_tmp[0] = c->d_field_tmp[1] = nullptr;
     c->d_dense = nullptr;
@@ -778,6 +781,7 @@ static int reset_world(uvt_ctx *c, uint32_t dim) {
     UVT_CUDA(c, cudaMalloc(&c->d_chunks, n_chunks * 4));
     UVT_CUDA(c, cudaMalloc(&c->d_chunks2, (size_t)(c->cd + 1) * (c->cd + 1) * (c->cd + 1) * 4));
     UVT_CUDA(c, cudaMalloc(&c->d_clear4, (size_t)(dim / 4) * (dim / 4) * 2));
+    UVT_CUDA(c, cudaMalloc(&c->d_clear16, (size_t)((dim + 15) / 16) * ((dim + 15) / 16) * 2));
     UVT_CUDA(c, cudaMalloc(&c->d_clear64, (size_t)((dim + 63) / 64) * ((dim + 63) / 64) * 2));
     return UVT_OK;
 }
@@ -1239,10 +1243,18 @@ int uvt_dispatch_frame(uvt_ctx *c) {
         // the three passes of game.zig:244-255 as three launches: measured faster than the fused kernel (c1 0.301 vs
         // 0.324 ms, c3 2.21 vs 2.41 ms) — the G-buffer round trip through L2 costs less than the registers and the
         // idle lanes of a kernel that keeps a primary and a shadow ray's state alive at once
-        rc = launch_primary<0>(c);
-        if (rc == UVT_OK) rc = launch_secondary<0>(c);
+        // (with timing on, every pass is bracketed by its own pair of events as well: uvt_last_pass_ms 0..2)
+        {
+            PassTimer tp(c, 0);
+            rc = launch_primary<0>(c);
+        }
+        if (rc == UVT_OK) {
+            PassTimer ts(c, 1);
+            rc = launch_secondary<0>(c);
+        }
         if (rc != UVT_OK) return rc;
         const uint32_t rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
+        PassTimer tb(c, 2);
         shade_kernel<<<dim3((c->W + 63) / 64, (rows + 3) / 4, c->layers), 256, 0, c->stream>>>(make_view(c, 0), g, make_target(c));
         return check_launch(c, "shade_kernel");
     }
@@ -1348,6 +1360,70 @@ int uvt_readback_async(uvt_ctx *c, uvt_buffer_kind kind, void *dst, size_t bytes
     UVT_CUDA(c, cudaMemcpyAsync(dst, c->snap[s], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
     UVT_CUDA(c, cudaEventRecord(c->snap_done[s], c->copy_stream));
     c->snap_busy[s] = true;
+    return UVT_OK;
+}
+
+// The band-partitioned FRAME of this ctx copied straight to where its bands belong in a full W x H host frame: every
+// rank of a tiled frame calls this on the SAME host frame (shared memory registered with uvt_host_register), so the
+// frame is assembled in host memory by N device-to-host copies running in parallel on N PCIe links — no GPU-to-GPU
+// exchange, no funnel through the presenting GPU.  Pipelined like uvt_readback_async (snapshot, copy stream).
+int uvt_readback_bands_async(uvt_ctx *c, void *host_frame, size_t frame_bytes) {
+    if (!c || !host_frame) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_REQUIRE(c, c->d_frame && c->layers == 1, "no single-layer frame buffer (uvt_resize first)");
+    UVT_REQUIRE(c, frame_bytes >= (size_t)c->W * c->H * 4, "host frame smaller than W*H*4 bytes");
+    const size_t row = (size_t)c->W * 4, rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part), bytes = rows * row;
+    if (bytes == 0) return UVT_OK;
+    const int s = c->snap_next;
+    c->snap_next ^= 1;
+    if (c->snap_busy[s]) {
+        UVT_CUDA(c, cudaEventSynchronize(c->snap_done[s]));
+        c->snap_busy[s] = false;
+    }
+    if (c->snap_bytes[s] < bytes) {
+        cudaFree(c->snap[s]);
+        c->snap[s] = nullptr;
+        c->snap_bytes[s] = 0;
+        UVT_CUDA(c, cudaMalloc(&c->snap[s], bytes));
+        c->snap_bytes[s] = bytes;
+    }
+    UVT_CUDA(c, cudaMemcpyAsync(c->snap[s], c->d_frame, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    UVT_CUDA(c, cudaEventRecord(c->snap_ready[s], c->stream));
+    UVT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->snap_ready[s], 0));
+    if (c->n_parts == 1) {
+        UVT_CUDA(c, cudaMemcpyAsync(host_frame, c->snap[s], (size_t)c->H * row, cudaMemcpyDeviceToHost, c->copy_stream));
+    } else {
+        // local band lb is global band lb * n_parts + part; all but possibly the frame's last band are full
+        const size_t band = (size_t)c->band_rows * row;
+        const uint32_t n_local = (uint32_t)(rows / c->band_rows);
+        const uint32_t last_global = (n_local - 1) * c->n_parts + c->part;
+        const uint32_t last_rows = std::min<uint32_t>(c->band_rows, c->H - last_global * c->band_rows);
+        const uint32_t n_full = last_rows == c->band_rows ? n_local : n_local - 1;
+        char *dst = (char *)host_frame + (size_t)c->part * band;
+        if (n_full)
+            UVT_CUDA(c, cudaMemcpy2DAsync(dst, band * c->n_parts, c->snap[s], band, band, n_full, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (n_full != n_local)
+            UVT_CUDA(c, cudaMemcpyAsync(dst + (size_t)n_full * band * c->n_parts, (char *)c->snap[s] + (size_t)n_full * band,
+                                        (size_t)last_rows * row, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    UVT_CUDA(c, cudaEventRecord(c->snap_done[s], c->copy_stream));
+    c->snap_busy[s] = true;
+    return UVT_OK;
+}
+
+// Page-lock caller memory (e.g. a POSIX shared-memory frame mapped by every rank) so that device-to-host copies into it
+// run asynchronously at full PCIe rate.
+int uvt_host_register(uvt_ctx *c, void *p, size_t bytes) {
+    if (!c || !p || !bytes) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_CUDA(c, cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return UVT_OK;
+}
+
+int uvt_host_unregister(uvt_ctx *c, void *p) {
+    if (!c || !p) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_CUDA(c, cudaHostUnregister(p));
     return UVT_OK;
 }
 

@@ -244,6 +244,17 @@ class Context:
         kind, _, _ = self._KINDS[name]
         self.check(self.L.uvt_readback_async(self.handle, kind, pinned.ctypes.data, pinned.nbytes))
 
+    def readback_bands_async(self, host_frame):
+        """This ctx's frame bands into their rows of a full W x H uint32 host frame (shared by all ranks of a tiled frame)."""
+        self.check(self.L.uvt_readback_bands_async(self.handle, host_frame.ctypes.data, host_frame.nbytes))
+
+    def host_register(self, arr):
+        """Page-lock caller memory (numpy array over e.g. a shared-memory mapping) for asynchronous device-to-host copies."""
+        self.check(self.L.uvt_host_register(self.handle, arr.ctypes.data, arr.nbytes))
+
+    def host_unregister(self, arr):
+        self.check(self.L.uvt_host_unregister(self.handle, arr.ctypes.data))
+
     def readback_wait(self):
         self.check(self.L.uvt_readback_wait(self.handle))
 

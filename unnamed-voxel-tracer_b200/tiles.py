@@ -73,3 +73,30 @@ def shard_poses(n_poses, world, rank):
     base, extra = divmod(n_poses, world)
     start = rank * base + min(rank, extra)
     return start, start + base + (1 if rank < extra else 0)
+
+
+class SharedHostFrame:
+    """One W x H RGBA8 frame in POSIX shared memory, mapped by every rank of a tiled frame.  Each rank page-locks its
+    mapping (Context.host_register) and copies its own bands into it (Context.readback_bands_async): the frame is
+    assembled in host memory by N parallel device-to-host copies."""
+
+    def __init__(self, name, W, H, create):
+        from multiprocessing import shared_memory
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=W * H * 4) if create else shared_memory.SharedMemory(name=name)
+        if not create:  # an attachment must not be unlinked by this process's resource tracker (Python < 3.13 registers it)
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.array = np.ndarray((H, W), dtype=np.uint32, buffer=self.shm.buf)
+        self.owner = create
+
+    def close(self):
+        self.array = None
+        try:
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+        except (FileNotFoundError, BufferError):
+            pass
