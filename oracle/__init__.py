@@ -73,6 +73,8 @@ def lib():
                                       ctypes.c_uint32, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_primary.argtypes = [ctypes.POINTER(_World), ctypes.c_void_p, ctypes.POINTER(_Params), ctypes.c_uint32, ctypes.c_uint32,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Counters)]
+        L.orc_primary_pixels.argtypes = [ctypes.POINTER(_World), ctypes.c_void_p, ctypes.POINTER(_Params), ctypes.c_uint32, ctypes.c_uint32,
+                                         ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_secondary.argtypes = [ctypes.POINTER(_World), ctypes.POINTER(_Params), ctypes.c_uint32, ctypes.c_uint32,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Counters)]
         L.orc_blit.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
@@ -150,6 +152,23 @@ def primary(world, cam, W, H, prm=None, want_hits=True):
     lib().orc_primary(ctypes.byref(world._c), cam.ctypes.data, ctypes.byref(prm), W, H, albedo.ctypes.data, normal.ctypes.data,
                       position.ctypes.data, hits.ctypes.data if want_hits else None, ctypes.byref(cnt))
     return {"albedo": albedo, "normal": normal, "position": position, "hits": hits, "counters": cnt.as_dict()}
+
+
+def primary_pixels(world, cam, W, H, xs, ys, prm=None):
+    """primary pass of the listed pixels of a W x H frame (sampled parity of frames too large for the CPU in test time);
+    every output is indexed by sample.  The shadow pass of the same samples is secondary() on the [1, n] arrays."""
+    prm = prm or params(world.dim)
+    cam = np.asarray(cam, dtype=CAMERA_DTYPE)
+    xs = np.ascontiguousarray(xs, dtype=np.uint32)
+    ys = np.ascontiguousarray(ys, dtype=np.uint32)
+    n = xs.size
+    albedo = np.empty(n, np.uint32)
+    normal = np.empty(n, np.uint32)
+    position = np.empty((n, 4), np.float32)
+    hits = np.empty(n, HIT_DTYPE)
+    lib().orc_primary_pixels(ctypes.byref(world._c), cam.ctypes.data, ctypes.byref(prm), W, H, n, xs.ctypes.data, ys.ctypes.data,
+                             albedo.ctypes.data, normal.ctypes.data, position.ctypes.data, hits.ctypes.data)
+    return {"albedo": albedo, "normal": normal, "position": position, "hits": hits}
 
 
 def secondary(world, normal, position, prm=None):

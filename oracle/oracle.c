@@ -278,6 +278,40 @@ static void merge_counters(orc_counters *dst, const orc_counters *src) {
     dst->early_out += src->early_out;
 }
 
+/* One pixel of primary.comp.glsl main (:23-69): G-buffer texels + the explicit hit record. */
+static void primary_pixel(const orc_world *w, const orc_camera *cam, const orc_params *prm, float thf, uint32_t W, uint32_t H,
+                          uint32_t px, uint32_t py, uint32_t *albedo, uint32_t *normal, float *position, orc_hit_rec *rec,
+                          orc_counters *cnt) {
+    float o[3], d[3], s[3];
+    orc_primary_ray(cam, thf, W, H, px, py, prm->map_dim, prm->epsilon, o, d, s);
+    orc_hit h;
+    orc_trace_map(w, s, d, (int)prm->primary_max_steps, &h);
+    add_counters(cnt, &h);
+    if (h.data != 0) { /* :58-62 */
+        *albedo = h.data;
+        *normal = pack_rgba8(h.normal[0], h.normal[1], h.normal[2], 1.0f);
+        for (int k = 0; k < 3; ++k) position[k] = ceilf(h.hit_pos[k]) / 8.0f;
+        position[3] = 1.0f;
+        const float dx = h.hit_pos[0] / 8.0f - o[0], dy = h.hit_pos[1] / 8.0f - o[1], dz = h.hit_pos[2] / 8.0f - o[2];
+        h.distance = sqrtf(dx * dx + dy * dy + dz * dz);
+    } else { /* :63-68 */
+        float sky[3];
+        orc_sky_dome2(d, sky);
+        *albedo = pack_rgba8(sky[0], sky[1], sky[2], 1.0f);
+        *normal = 0xFFFFFFFFu;
+        for (int k = 0; k < 4; ++k) position[k] = -1.0f;
+    }
+    if (rec) {
+        rec->px = h.p[0]; rec->py = h.p[1]; rec->pz = h.p[2];
+        rec->block = h.block;
+        rec->color = h.data;
+        rec->distance = h.distance;
+        rec->trips = (uint16_t)h.trips;
+        rec->face = (uint8_t)h.face;
+        rec->exit_kind = (uint8_t)h.exit_kind;
+    }
+}
+
 /* primary.comp.glsl main: :23-69.  Row 0 is the bottom image row. */
 void orc_primary(const orc_world *w, const orc_camera *cam, const orc_params *prm, uint32_t W, uint32_t H,
                  uint32_t *albedo, uint32_t *normal, float *position, orc_hit_rec *hits, orc_counters *counters) {
@@ -291,42 +325,29 @@ void orc_primary(const orc_world *w, const orc_camera *cam, const orc_params *pr
 #pragma omp for schedule(dynamic, 4)
         for (int64_t py = 0; py < (int64_t)H; ++py) {
             for (uint32_t px = 0; px < W; ++px) {
-                float o[3], d[3], s[3];
-                orc_primary_ray(cam, thf, W, H, px, (uint32_t)py, prm->map_dim, prm->epsilon, o, d, s);
-                orc_hit h;
-                orc_trace_map(w, s, d, (int)prm->primary_max_steps, &h);
-                add_counters(&local, &h);
                 const size_t i = (size_t)py * W + px;
-                if (h.data != 0) { /* :58-62 */
-                    albedo[i] = h.data;
-                    normal[i] = pack_rgba8(h.normal[0], h.normal[1], h.normal[2], 1.0f);
-                    for (int k = 0; k < 3; ++k) position[4 * i + k] = ceilf(h.hit_pos[k]) / 8.0f;
-                    position[4 * i + 3] = 1.0f;
-                    const float dx = h.hit_pos[0] / 8.0f - o[0], dy = h.hit_pos[1] / 8.0f - o[1], dz = h.hit_pos[2] / 8.0f - o[2];
-                    h.distance = sqrtf(dx * dx + dy * dy + dz * dz);
-                } else { /* :63-68 */
-                    float sky[3];
-                    orc_sky_dome2(d, sky);
-                    albedo[i] = pack_rgba8(sky[0], sky[1], sky[2], 1.0f);
-                    normal[i] = 0xFFFFFFFFu;
-                    for (int k = 0; k < 4; ++k) position[4 * i + k] = -1.0f;
-                }
-                if (hits) {
-                    orc_hit_rec *r = &hits[i];
-                    r->px = h.p[0]; r->py = h.p[1]; r->pz = h.p[2];
-                    r->block = h.block;
-                    r->color = h.data;
-                    r->distance = h.distance;
-                    r->trips = (uint16_t)h.trips;
-                    r->face = (uint8_t)h.face;
-                    r->exit_kind = (uint8_t)h.exit_kind;
-                }
+                primary_pixel(w, cam, prm, thf, W, H, px, (uint32_t)py, &albedo[i], &normal[i], &position[4 * i], hits ? &hits[i] : NULL, &local);
             }
         }
 #pragma omp critical
         merge_counters(&total, &local);
     }
     if (counters) *counters = total;
+}
+
+/* The same for a LIST of pixels of the W x H frame (sampled parity checks of frames too large to render whole on the
+ * CPU in test time): outputs are indexed by sample. */
+void orc_primary_pixels(const orc_world *w, const orc_camera *cam, const orc_params *prm, uint32_t W, uint32_t H, size_t n,
+                        const uint32_t *xs, const uint32_t *ys, uint32_t *albedo, uint32_t *normal, float *position, orc_hit_rec *hits) {
+    const float thf = tanf(cam->fov / 2.0f);
+#pragma omp parallel
+    {
+        orc_counters local;
+        memset(&local, 0, sizeof local);
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t i = 0; i < (int64_t)n; ++i)
+            primary_pixel(w, cam, prm, thf, W, H, xs[i], ys[i], &albedo[i], &normal[i], &position[4 * i], hits ? &hits[i] : NULL, &local);
+    }
 }
 
 /* secondary.comp.glsl main: :18-51 */

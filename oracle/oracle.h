@@ -69,6 +69,8 @@ void orc_primary_ray(const orc_camera *cam, float tan_half_fov, uint32_t W, uint
                      uint32_t map_dim, float epsilon, float origin[3], float dir[3], float start[3]);
 void orc_primary(const orc_world *w, const orc_camera *cam, const orc_params *prm, uint32_t W, uint32_t H,
                  uint32_t *albedo, uint32_t *normal, float *position, orc_hit_rec *hits, orc_counters *counters);
+void orc_primary_pixels(const orc_world *w, const orc_camera *cam, const orc_params *prm, uint32_t W, uint32_t H, size_t n,
+                        const uint32_t *xs, const uint32_t *ys, uint32_t *albedo, uint32_t *normal, float *position, orc_hit_rec *hits);
 void orc_secondary(const orc_world *w, const orc_params *prm, uint32_t W, uint32_t H,
                    const uint32_t *normal, const float *position, uint32_t *illum, orc_counters *counters);
 void orc_blit(uint32_t W, uint32_t H, const uint32_t *albedo, const uint32_t *normal, const float *position,

@@ -95,8 +95,12 @@ def test_committed_golden_fixture(uvt, oracle, w1):
     for name, cam in (("k0_96x54", camera_k0(oracle)), ("k1_96x54", camera_k1(uvt, oracle))):
         gold = np.load(os.path.join(GOLDEN, f"oracle_w1_{name}.npz"))
         g = gpu_render(ctx, cam)
-        assert np.array_equal(g["hits"].view(np.uint8).reshape(-1), gold["hits"].view(np.uint8).reshape(-1)) or \
-            ulp_diff(g["hits"]["distance"], gold["hits"].view(g["hits"].dtype).reshape(54, 96)["distance"]).max() <= 2
+        gh = gold["hits"].view(g["hits"].dtype).reshape(54, 96)
+        for f in ("px", "py", "pz", "block", "color", "face", "trips", "exit_kind"):
+            assert np.array_equal(g["hits"][f], gh[f]), f
+        hit = gh["face"] != 0
+        assert ulp_diff(g["hits"]["distance"][hit], gh["distance"][hit]).max(initial=0) <= 2 and (g["hits"]["distance"][~hit] == -1.0).all()
+        assert np.array_equal(g["albedo"][hit], gold["albedo"][hit]) and channel_diff(g["albedo"], gold["albedo"]).max() <= 1
         for k in ("normal", "illumination"):
             assert np.array_equal(g[k], gold[k])
         assert np.array_equal(g["position"].view(np.uint32), gold["position"].view(np.uint32))
@@ -201,6 +205,26 @@ def test_camera_outside_and_degenerate_views(uvt, oracle, w1):
         r = oracle.render(sc.oracle_world, cam, 128, 72)
         assert_primary_parity(g, r)
         assert np.array_equal(g["illumination"], r["illumination"])
+
+
+def test_entity_boxes_shadow_as_lines(uvt, oracle, w1):
+    """traceEntities (map.glsl:172-201): the five unit boxes shadow as LINES, boxes behind the origin included.  Two cameras whose
+    frames hold many pixels that only the entities put in shadow (oracle with entities on vs off), against the GPU."""
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    ctx.resize(256, 144)
+    down = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, -1, 0, 0], [0, 0, 0, 1]], np.float32)
+    for cam, least in ((oracle.make_camera((256.0, 30.0, 256.0), down), 150),
+                       (oracle.make_camera((262.0, 30.0, 262.0), pitch_yaw_matrix(uvt, 0.6, 5 * np.pi / 4)), 300),
+                       (oracle.make_camera((249.0, 27.0, 262.0), pitch_yaw_matrix(uvt, 0.9, 2.2)), 1)):
+        g = gpu_render(ctx, cam)
+        r = oracle.render(sc.oracle_world, cam, 256, 144)
+        off = oracle.render(sc.oracle_world, cam, 256, 144, oracle.params(512, entities=False))
+        n_entity = int((r["illumination"] != off["illumination"]).sum())
+        assert n_entity >= least, n_entity
+        assert np.array_equal(g["illumination"], r["illumination"])
+        assert_primary_parity(g, r)
+        assert channel_diff(g["frame"], r["frame"]).max() <= 1
 
 
 def test_empty_world_and_single_block(uvt, oracle, scene_factory):
@@ -427,6 +451,51 @@ def test_full_size_layouts_agree_and_rows_match_oracle(uvt, oracle, w1, size):
         assert ca == r["primary_counters"]
 
 
+@pytest.mark.parametrize("size", [(1280, 720), (1920, 1080)])
+def test_c1_c2_bench_frames_full_size(uvt, oracle, w1, size):
+    """BASELINE configs 1 and 2 exactly as bench.py renders them: W1, camera K0, full size, every pixel against the oracle."""
+    ctx, sc = w1
+    W, H = size
+    ctx.set_layout("compact")
+    ctx.resize(W, H)
+    cam = camera_k0(oracle)
+    g = gpu_render(ctx, cam)
+    r = oracle.render(sc.oracle_world, cam, W, H)
+    assert_primary_parity(g, r)
+    assert np.array_equal(g["illumination"], r["illumination"])
+    assert channel_diff(g["frame"], r["frame"]).max() <= 1
+    assert ctx.count_pass("primary") == r["primary_counters"] and ctx.count_pass("secondary") == r["secondary_counters"]
+
+
+def test_c4_8k_frame_tiled_full_size(uvt, oracle, w1):
+    """BASELINE config 4: the 7680x4320 frame of W1 / K1 rendered as 8 interleaved 32-row band partitions (what 8 ranks render),
+    assembled, and every one of its 33 M pixels compared with the oracle: hit records, G-buffer, illumination, shaded frame."""
+    ctx, sc = w1
+    W, H, band, n_parts = 7680, 4320, 32, 8
+    cam = camera_k1(uvt, oracle)
+    ctx.set_layout("compact")
+    r = oracle.render(sc.oracle_world, cam, W, H)
+    ctx.set_partition(band, n_parts, 0)
+    ctx.resize(W, H)
+    rows_seen = np.zeros(H, bool)
+    try:
+        for part in range(n_parts):
+            ctx.set_partition(band, n_parts, part)
+            g = gpu_render(ctx, cam)
+            gy = uvt.tiles.local_to_global_rows(H, band, n_parts, part, g["frame"].shape[0])
+            ok = gy >= 0
+            rows = gy[ok]
+            rows_seen[rows] = True
+            part_ref = {k: r[k][rows] for k in ("albedo", "normal", "position", "hits")}
+            assert_primary_parity({k: g[k][ok] for k in ("albedo", "normal", "position", "hits")}, part_ref)
+            assert np.array_equal(g["illumination"][ok], r["illumination"][rows])
+            assert channel_diff(g["frame"][ok], r["frame"][rows]).max() <= 1
+    finally:
+        ctx.set_partition(8, 1, 0)
+        ctx.resize(64, 64)
+    assert rows_seen.all()
+
+
 # ---- W4 (procgen 2048) and the sealed-ray / free-trip machinery ----------------------------------------
 @pytest.fixture(scope="module")
 def w4(uvt, scene_factory):
@@ -454,6 +523,149 @@ def test_w4_world_parity(uvt, oracle, w4):
     for cam in uvt.scenes.sweep_poses(2048, 6):
         g = gpu_render(ctx, cam)
         assert_primary_parity(g, oracle.render(sc.oracle_world, cam, 160, 90, prm))
+
+
+def test_c3_4k_frame_full_size(uvt, oracle, w4):
+    """BASELINE config 3 exactly as bench.py renders it: W4, camera K1, 3840x2160, every pixel of the primary, shadow and
+    shade passes against the oracle (the oracle needs a few seconds for the 8.3 M + 5 M rays)."""
+    ctx, sc = w4
+    W, H = 3840, 2160
+    cam = uvt.scenes.camera_k1(2048)
+    prm = oracle.params(2048)
+    ctx.resize(W, H)
+    g = gpu_render(ctx, cam)
+    r = oracle.render(sc.oracle_world, cam, W, H, prm)
+    assert_primary_parity(g, r)
+    assert np.array_equal(g["illumination"], r["illumination"])
+    assert channel_diff(g["frame"], r["frame"]).max() <= 1
+    assert ctx.count_pass("primary") == r["primary_counters"] and ctx.count_pass("secondary") == r["secondary_counters"]
+    ctx.resize(64, 64)
+
+
+def test_c5_pose_sweep_full_size(uvt, oracle, w4):
+    """BASELINE config 5: the 256 LCG-seeded poses over W4 at 1920x1080.  Every pose is rendered on the GPU; 12 of them are
+    compared with the oracle pixel for pixel, all 256 on 600 random pixels each (153,600 rays: primary record + shadow texel)."""
+    ctx, sc = w4
+    W, H = 1920, 1080
+    prm = oracle.params(2048)
+    poses = uvt.scenes.sweep_poses(2048, 256)
+    ctx.resize(W, H)
+    rng = np.random.default_rng(55)
+    n_hits = 0
+    for i, cam in enumerate(poses):
+        g = gpu_render(ctx, cam)
+        if i % 22 == 3:
+            r = oracle.render(sc.oracle_world, cam, W, H, prm)
+            assert_primary_parity(g, r)
+            assert np.array_equal(g["illumination"], r["illumination"])
+            assert channel_diff(g["frame"], r["frame"]).max() <= 1
+        xs, ys = rng.integers(0, W, 600), rng.integers(0, H, 600)
+        p = oracle.primary_pixels(sc.oracle_world, cam, W, H, xs, ys, prm)
+        gh = g["hits"][ys, xs]
+        for f in ("px", "py", "pz", "block", "color", "face", "trips", "exit_kind"):
+            assert np.array_equal(gh[f], p["hits"][f]), (i, f)
+        hit = p["hits"]["face"] != 0
+        n_hits += int(hit.sum())
+        assert ulp_diff(gh["distance"][hit], p["hits"]["distance"][hit]).max(initial=0) <= 2
+        assert np.array_equal(g["normal"][ys, xs], p["normal"])
+        assert np.array_equal(g["position"][ys, xs].view(np.uint32), p["position"].view(np.uint32))
+        s = oracle.secondary(sc.oracle_world, p["normal"][None, :], p["position"][None, :, :], prm)
+        assert np.array_equal(g["illumination"][ys, xs], s["illumination"][0]), i
+    assert n_hits > 40000
+    ctx.resize(64, 64)
+
+
+def _line_hugging_world(uvt, oracle, rng, cam, W, H, n_rays, kinds):
+    """Blocks placed 1-2 blocks beside / below the lines of random rays of the frame, at random distances along them: thin
+    pillars up to just under the line, slabs and overhangs next to it.  The sealed-ray and free-run proofs of
+    line_free_trips() must hold against geometry that hugs the rays they are about to skip."""
+    cells = []
+    for _ in range(n_rays):
+        x, y = int(rng.integers(0, W)), int(rng.integers(0, H))
+        o, d, s = oracle.primary_ray(cam, W, H, x, y, 512)
+        t = float(rng.uniform(8.0, 185.0))
+        p = np.asarray(s, np.float64) + np.asarray(d, np.float64) * t / max(float(np.abs(d).sum()), 1e-6)  # about t trips along the ray
+        kind = kinds[int(rng.integers(0, len(kinds)))]
+        off = rng.integers(1, 3)  # 1 or 2 blocks off the line
+        bx, by, bz = int(np.floor(p[0])), int(np.floor(p[1])), int(np.floor(p[2]))
+        if kind == "pillar":      # a column from the ground to `off` blocks under the line
+            cells += [(bx, yy, bz) for yy in range(max(by - off - int(rng.integers(0, 12)), 0), by - off + 1)]
+        elif kind == "beside":    # a block at the line's height, `off` blocks to the side
+            ax = int(rng.integers(0, 2))
+            cells.append((bx + (off if ax == 0 else 0) * (1 if rng.random() < 0.5 else -1), by, bz + (off if ax == 1 else 0) * (1 if rng.random() < 0.5 else -1)))
+        elif kind == "slab":      # a 3x3 slab `off` blocks under the line
+            cells += [(bx + i, by - off, bz + j) for i in range(-1, 2) for j in range(-1, 2)]
+        elif kind == "overhang":  # a slab `off` blocks ABOVE the line (the column tops then lie above the ray)
+            cells += [(bx + i, by + off, bz + j) for i in range(-1, 2) for j in range(-1, 2)]
+        elif kind == "on":        # a block the ray does meet
+            cells.append((bx, by, bz))
+    return [(x, y, z) for (x, y, z) in cells if 0 <= x < 512 and 0 <= y < 512 and 0 <= z < 512]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_line_walk_against_ray_hugging_geometry(uvt, oracle, scene_factory, seed):
+    """Adversarial worlds for the column-tops walk (sealed rays, long free runs): geometry placed one or two blocks off the
+    lines of the very rays being traced — climbing, level and descending, lattice-aligned and generic camera positions — with
+    and without a ground plane.  Fast path == verbatim-trips kernel (reference layout) == oracle, primary and shadow pass."""
+    rng = np.random.default_rng(1000 + seed)
+    W, H = 192, 108
+    V = uvt.voxel.Voxel
+    lattice = seed % 2 == 0
+    pos = (256.0, 40.0 + 8 * seed, 256.0) if lattice else (float(rng.uniform(200, 312)), float(rng.uniform(20, 120)), float(rng.uniform(200, 312)))
+    pitch = [-0.5, -0.15, 0.0, 0.12, 0.35, 0.7][seed]
+    cam = oracle.make_camera(pos, pitch_yaw_matrix(uvt, pitch, float(rng.uniform(0, 2 * np.pi))), fov=float(rng.uniform(0.9, 1.9)))
+    kinds = [["pillar", "beside", "slab", "on"], ["pillar", "beside", "slab", "overhang", "on"]][seed % 2]
+
+    def fill(bm):
+        if seed % 3 != 2:   # a ground plane 20-60 blocks under the camera, so that descending rays have something to approach
+            gy = max(int(pos[1]) - int(rng.integers(20, 60)), 0)
+            for x in range(176, 336, 1):
+                for z in range(176, 336, 1):
+                    bm.set(x, gy, z, V(21 + (x + z) % 3, True))
+        for (x, y, z) in _line_hugging_world(uvt, oracle, rng, cam, W, H, 140, kinds):
+            bm.set(x, y, z, V(int(rng.integers(0, 29)), True))
+
+    with uvt.Context(0, hit_buffer=True) as ctx:
+        sc = scene_factory(512, fill, ctx=ctx)
+        ctx.resize(W, H)
+        ctx.set_layout("compact")
+        a = gpu_render(ctx, cam)
+        ctx.set_layout("reference")
+        b = gpu_render(ctx, cam)
+        ctx.set_layout("compact")
+        assert np.array_equal(a["hits"].view(np.uint8), b["hits"].view(np.uint8))
+        for k in ("albedo", "normal", "illumination", "frame"):
+            assert np.array_equal(a[k], b[k]), k
+        r = oracle.render(sc.oracle_world, cam, W, H)
+        assert_primary_parity(a, r)
+        assert np.array_equal(a["illumination"], r["illumination"])
+        stats, exact = ctx.fetch_stats("primary"), ctx.count_pass("primary")
+        assert stats["lookups"] < exact["t_in"]   # the walk and the clearances did skip fetches in this world
+
+
+def test_line_walk_w4_near_map_faces_and_lattice_origins(uvt, oracle, w4):
+    """W4 cameras a few blocks from the map faces and on lattice points, looking out, along and into the map, up and down:
+    the walk must stop proving at the faces (a ray that leaves the map is an exit, not an iteration-cap miss)."""
+    ctx, sc = w4
+    prm = oracle.params(2048)
+    ctx.resize(160, 90)
+    rng = np.random.default_rng(77)
+    cams = []
+    for (x, z) in ((3.0, 1000.0), (2044.5, 700.25), (900.0, 2.0), (1200.0, 2045.0), (4.0, 4.0), (2040.0, 2040.0), (1024.0, 1024.0)):
+        h = max(uvt.procgen.height(2048, int(x), int(z)), 16)
+        for k in range(3):
+            cams.append(oracle.make_camera((x, float(h + rng.integers(2, 60)), z),
+                                           pitch_yaw_matrix(uvt, float(rng.uniform(-0.9, 0.9)), float(rng.uniform(0, 2 * np.pi))), fov=float(rng.uniform(0.7, 2.0))))
+    cams.append(oracle.make_camera((1024.0, 2040.0, 1024.0), pitch_yaw_matrix(uvt, -0.4, 1.0)))   # just under the top face, looking up
+    cams.append(oracle.make_camera((1024.0, 2040.0, 1024.0), pitch_yaw_matrix(uvt, 1.2, 1.0)))    # ... and down
+    n_exit = 0
+    for cam in cams:
+        g = gpu_render(ctx, cam)
+        r = oracle.render(sc.oracle_world, cam, 160, 90, prm)
+        assert_primary_parity(g, r)
+        assert np.array_equal(g["illumination"], r["illumination"])
+        n_exit += int((r["hits"]["exit_kind"] == 2).sum())
+    assert n_exit > 20000   # the faces were exercised
 
 
 def test_sealed_rays_and_map_faces(uvt, oracle, w1):

@@ -237,3 +237,19 @@ def test_oracle_reproduces_committed_golden(uvt, oracle, world512, name):
         assert np.array_equal(r[k], g[k]), k
     assert np.array_equal(r["hits"].view(np.uint8), g["hits"].view(np.uint8).reshape(r["hits"].view(np.uint8).shape))
     assert [r["primary_counters"][k] for k in ("rays", "t_in", "t_chunk", "t_block", "hits")] == g["primary_counters"].tolist()
+
+
+def test_pixel_list_api_equals_the_full_frame(oracle, world512, uvt):
+    """orc_primary_pixels (sampled parity of the 4K / 8K frames) is the same code path as the full-frame pass."""
+    cam = camera_k1(uvt, oracle)
+    W, H = 200, 120
+    full = oracle.render(world512.oracle_world, cam, W, H)
+    rng = np.random.default_rng(3)
+    xs, ys = rng.integers(0, W, 3000), rng.integers(0, H, 3000)
+    p = oracle.primary_pixels(world512.oracle_world, cam, W, H, xs, ys)
+    assert np.array_equal(p["hits"], full["hits"][ys, xs])
+    for k in ("albedo", "normal"):
+        assert np.array_equal(p[k], full[k][ys, xs])
+    assert np.array_equal(p["position"].view(np.uint32), full["position"][ys, xs].view(np.uint32))
+    s = oracle.secondary(world512.oracle_world, p["normal"][None, :], p["position"][None, :, :])
+    assert np.array_equal(s["illumination"][0], full["illumination"][ys, xs])
