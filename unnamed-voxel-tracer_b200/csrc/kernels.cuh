@@ -57,6 +57,13 @@ __device__ __forceinline__ uint32_t pack_rgba8(float r, float g, float b, float 
     return unorm8(r) | (unorm8(g) << 8) | (unorm8(b) << 16) | (unorm8(a) << 24);
 }
 
+// RGBA8 UNORM fetch: c / 255 (correctly rounded).  The normals the primary pass stores are 0 or 255: no division for those.
+__device__ __forceinline__ float unorm8_to_float(uint32_t c) {
+    if (c == 0u) return 0.0f;
+    if (c == 255u) return 1.0f;
+    return (float)c / 255.0f;
+}
+
 // SkyDome2: camera.glsl:11-19 (rgb; alpha is 1).  pow(sun, 8) and pow(sun, 3) are integer
 // powers evaluated by multiplication (within the 1/255 shading tolerance of the oracle's powf).
 __device__ __forceinline__ void sky_dome2(float rx, float ry, float rz, float &r, float &g, float &b) {
@@ -89,8 +96,16 @@ __device__ __forceinline__ bool trace_entities(float ox, float oy, float oz, flo
     const float P[5][3] = {{256.f, 21.f, 256.f}, {251.f, 21.f, 259.f}, {253.f, 21.f, 256.f}, {251.f, 21.f, 256.f}, {257.f, 21.f, 261.f}};
     float prev_d = __int_as_float(0x7f800000);
     bool any = false;
+    const float dd = dx * dx + dy * dy + dz * dz;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
+        {   // A line further than 1 block from the box centre misses the unit box (half diagonal 0.866): its slab intervals are
+            // apart by more than 0.13 / |d| in parameter, far beyond the rounding of the exact test below (< 1e-3 at map scale),
+            // so that test would find tf < tn.  The cross product decides it without the six divisions.
+            const float vx = P[i][0] + 0.5f - ox, vy = P[i][1] + 0.5f - oy, vz = P[i][2] + 0.5f - oz;
+            const float cx = vy * dz - vz * dy, cy = vz * dx - vx * dz, cz = vx * dy - vy * dx;
+            if (cx * cx + cy * cy + cz * cz > dd) continue;
+        }
         const float ex = ox - P[i][0], ey = oy - P[i][1], ez = oz - P[i][2];
         const float dist = sqrtf(ex * ex + ey * ey + ez * ez);
         if (dist >= max_distance) continue;
@@ -124,6 +139,17 @@ __device__ __forceinline__ void primary_ray(const CamDev &cam, const ViewDev &v,
     const float len = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     dx = q[0] / len; dy = q[1] / len; dz = q[2] / len;
     const float D = (float)v.map_dim;
+    // A camera strictly inside the map (the game's case) has tNear < 0 for every finite direction: per axis one of (0 - o) / d,
+    // (D - o) / d is negative (or -inf for d = +-0), so max(tNear, 0) = 0 and the start point is o + d * 0 - EPSILON = o - EPSILON
+    // (o != 0; d * 0 = +-0).  The six divisions of the slab test are only run when that does not hold.
+    const bool inside = cam.pos[0] > 0.0f && cam.pos[0] < D && cam.pos[1] > 0.0f && cam.pos[1] < D && cam.pos[2] > 0.0f && cam.pos[2] < D;
+    const float inf = __int_as_float(0x7f800000);
+    if (inside && fabsf(dx) < inf && fabsf(dy) < inf && fabsf(dz) < inf) {
+        sx = cam.pos[0] - v.epsilon;
+        sy = cam.pos[1] - v.epsilon;
+        sz = cam.pos[2] - v.epsilon;
+        return;
+    }
     float tn, tf;
     intersect_aabb(cam.pos[0], cam.pos[1], cam.pos[2], dx, dy, dz, 0.0f, 0.0f, 0.0f, D, D, D, tn, tf);
     const float t0 = gmax(tn, 0.0f);
@@ -183,6 +209,9 @@ __device__ __forceinline__ void tile_pixel(uint32_t &x, uint32_t &ly) {
 }
 
 __device__ __forceinline__ void stage_masks(uint32_t *smem, const uint32_t *__restrict__ gmasks, uint32_t n_mats) {
+#if !UVT_SMEM_MASKS
+    return;
+#endif
     // only the materials in use, at most kSmemMaskMats: (n_mats + 1) x 16 words (id 0 is the empty block)
     const uint32_t n = min(n_mats + 1u, (uint32_t)kSmemMaskMats) * 16u;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) smem[i] = __ldg(&gmasks[i]);
@@ -215,7 +244,7 @@ struct WorldArgs<WorldDense> {
 template <class World, int COUNT, bool HITBUF, bool BATCH>
 __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) primary_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0,
                                                            ViewDev v, GBufDev gb, DevCounters *counters) {
-    __shared__ uint32_t s_masks[kIsCompact<World> ? kSmemMaskMats * 16 : 1];
+    __shared__ uint32_t s_masks[(UVT_SMEM_MASKS && kIsCompact<World>) ? kSmemMaskMats * 16 : 1];
     World w = wa.w;
     if constexpr (kIsCompact<World>) {
         stage_masks(s_masks, wa.masks, wa.n_mats);
@@ -272,11 +301,11 @@ __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) primary_kernel(World
 template <class World, int COUNT>
 __device__ __forceinline__ uint32_t shadow_pixel(const World &w, bool active, const ViewDev &v, float posx, float posy, float posz,
                                                  uint32_t normal, TripCounts &tc, uint32_t &hit) {
-    const float nx = (float)(normal & 255u) / 255.0f, ny = (float)((normal >> 8) & 255u) / 255.0f,
-                nz = (float)((normal >> 16) & 255u) / 255.0f;
+    const float nx = unorm8_to_float(normal & 255u), ny = unorm8_to_float((normal >> 8) & 255u), nz = unorm8_to_float((normal >> 16) & 255u);
     const float ox = posx + nx * 0.001f, oy = posy + ny * 0.001f, oz = posz + nz * 0.001f;
     Hit h;
-    trace<World, COUNT>(w, active, ox, oy, oz, UVT_SUN_X, UVT_SUN_Y, UVT_SUN_Z, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);  // all 32 lanes
+    // (the sun clearance map is built for the step cap in force: uvt.cu rebuilds it when the cap grows)
+    trace<World, COUNT, true>(w, active, ox, oy, oz, UVT_SUN_X, UVT_SUN_Y, UVT_SUN_Z, (int)v.max_steps, (int)(8u * v.map_dim), h, tc);  // all 32 lanes
     if (!active) { hit = 0; return 0u; }
     hit = h.data != 0;
     bool shadowed = h.data != 0;
@@ -291,7 +320,7 @@ __device__ __forceinline__ uint32_t shadow_pixel(const World &w, bool active, co
 // ---- secondary pass ------------------------------------------------------------------------
 template <class World, int COUNT>
 __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) secondary_kernel(WorldArgs<World> wa, ViewDev v, GBufDev gb, DevCounters *counters) {
-    __shared__ uint32_t s_masks[kIsCompact<World> ? kSmemMaskMats * 16 : 1];
+    __shared__ uint32_t s_masks[(UVT_SMEM_MASKS && kIsCompact<World>) ? kSmemMaskMats * 16 : 1];
     World w = wa.w;
     if constexpr (kIsCompact<World>) {
         stage_masks(s_masks, wa.masks, wa.n_mats);
@@ -373,7 +402,7 @@ __global__ void __launch_bounds__(256) shade_kernel(ViewDev v, GBufDev gb, Frame
 template <class World, bool GBUF, bool BATCH>
 __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS_FRAME) frame_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0, ViewDev v,
                                                          uint32_t shadow_steps, GBufDev gb, FrameTarget ft) {
-    __shared__ uint32_t s_masks[kIsCompact<World> ? kSmemMaskMats * 16 : 1];
+    __shared__ uint32_t s_masks[(UVT_SMEM_MASKS && kIsCompact<World>) ? kSmemMaskMats * 16 : 1];
     World w = wa.w;
     if constexpr (kIsCompact<World>) {
         stage_masks(s_masks, wa.masks, wa.n_mats);
@@ -429,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS_FRAME) frame_kernel(W
 // terrain_edit.comp.glsl:10-17: the centre pick ray (rayUV = 0)
 template <class World>
 __global__ void pick_kernel(WorldArgs<World> wa, CamDev cam, ViewDev v, uint8_t *out_hit) {
-    __shared__ uint32_t s_masks[kIsCompact<World> ? kSmemMaskMats * 16 : 1];
+    __shared__ uint32_t s_masks[(UVT_SMEM_MASKS && kIsCompact<World>) ? kSmemMaskMats * 16 : 1];
     World w = wa.w;
     if constexpr (kIsCompact<World>) {
         stage_masks(s_masks, wa.masks, wa.n_mats);
@@ -636,6 +665,38 @@ __global__ void coarse_clear_kernel(const uint16_t *__restrict__ in, uint16_t *_
     for (int z = 4 * cz; z < min(4 * cz + 4, in_dim); ++z)
         for (int x = 4 * cx; x < min(4 * cx + 4, in_dim); ++x) m = max(m, (unsigned int)in[x + in_dim * z]);
     out[i] = (uint16_t)m;
+}
+
+// Sun clearance of the shadow pass.  Every shadow ray has the direction SUN_DIR = (s, u, s), all components positive, so
+// what line_free_trips() would find for it depends only on where it starts.  For a ray whose state P lies in column group q:
+// the line runs along the diagonal of the x-z plane and enters group c = q + (a, b) (a, b >= 0, |a - b| <= 1) after an
+// x-advance of at least 4 * max(max(a, b) - 1, 0) blocks, i.e. a climb of at least that times u / s; travelling up every
+// axis the state is ON the line (no 0.999-reset drift), and a lookup names the line's block or, by the round-up carry, a
+// neighbour one block over: clear4 is grown by one block.  So with
+//     sun4[q] = max over the groups c within reach of  clear4[c] - (u / s) * 4 * max(max(a, b) - 1, 0)      (rounded up)
+// a state in a block row ABOVE sun4[q] looks up nothing but empty blocks for `steps` trips; groups beyond the x / z faces
+// make the value infinite (the ray could leave the map), the top face is the caller's sun_row_max.  Reach: `steps` trips
+// cover at most (steps + 5) / (2 s + u) of parameter, s times that along x.
+__global__ void sun_clear_kernel(const uint16_t *__restrict__ clear4, uint16_t *__restrict__ sun4, int qdim, int steps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= qdim * qdim) return;
+    const int qx = i % qdim, qz = i / qdim;
+    const float reach_x = UVT_SUN_X * (float)(steps + 5) / (2.0f * UVT_SUN_X + UVT_SUN_Y);  // blocks along x (= along z)
+    const int K = (int)(reach_x * 0.25f) + 2;                                                // groups ahead that the line may reach
+    const float climb = UVT_SUN_Y / UVT_SUN_X * 4.0f;
+    float m = 0.0f;
+    bool open = false;
+    for (int k = 0; k <= K; ++k) {
+        const float rise = climb * (float)max(k - 1, 0);
+        for (int j = 0; j < 3; ++j) {  // (a, b) = (k, k), (k, k - 1), (k - 1, k)
+            const int a = j == 2 ? k - 1 : k, b = j == 1 ? k - 1 : k;
+            if (a < 0 || b < 0) continue;
+            const int cx = qx + a, cz = qz + b;
+            if (cx >= qdim || cz >= qdim) { open = true; continue; }
+            m = fmaxf(m, (float)clear4[cx + qdim * cz] - rise);
+        }
+    }
+    sun4[i] = open ? (uint16_t)0xFFFF : (uint16_t)min((int)ceilf(m), 0xFFFE);
 }
 
 // Block-level clearance.  One CTA per brick, one thread per block.  The occupancy of the 5x5x5 chunk

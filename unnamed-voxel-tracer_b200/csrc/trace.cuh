@@ -27,7 +27,11 @@ struct Hit {
     uint32_t exit_kind;  // 0 hit, 1 cap, 2 left the map
 };
 
-constexpr int kSmemMaskMats = 64;  // sub-voxel masks of material ids < 64 are staged in shared memory, the rest read through L1
+#ifndef UVT_SMEM_MASKS
+#define UVT_SMEM_MASKS 0  // 1: experiment build that stages the occupancy masks in shared memory per CTA.  Measured 7 % SLOWER on every
+                          // config (c3 1.647 vs 1.530 ms): the 2 KB in use stay L1-resident anyway, and the staging costs a barrier per CTA
+#endif
+constexpr int kSmemMaskMats = 64;  // (UVT_SMEM_MASKS build) masks of material ids < 64 are staged in shared memory, the rest read through L1
 
 struct TripCounts {
     uint32_t t_in, t_chunk, t_block;
@@ -90,6 +94,9 @@ struct WorldCompact {
                                             // kMatLimit + min(n_free, 30)) without the chunk indirection; nullptr when not built
     const uint16_t *__restrict__ clear64;   // [ceil(dim/64)^2] maximum of clear4 over 64x64-block column groups (coarsest level of the walk)
     const uint16_t *__restrict__ clear16;   // [ceil(dim/16)^2] ... over 16x16-block column groups
+    const uint16_t *__restrict__ sun4;      // [(dim/4)^2] sun clearance: a SUN_DIR ray whose state lies in this column group, in a block row
+                                            // ABOVE this value, meets nothing but empty in-map blocks for sun_steps trips (sun_clear_kernel)
+    int32_t sun_row_max;                    // ... provided its block row is at most this (the ray stays under the top face)
     const uint16_t *__restrict__ clear4;    // [(dim/4)^2] per 4x4-block column group, grown by one block on every side:
                                             // every block with y >= clear4 there is empty (sky_sealed)
 
@@ -113,7 +120,11 @@ struct WorldCompact {
     }
     __device__ __forceinline__ uint32_t block_word(uint32_t mat) const { return __ldg(&mat_word[mat]); }
     __device__ __forceinline__ uint32_t mask_word(uint32_t mat, uint32_t bit) const {
+#if UVT_SMEM_MASKS
         return mat < (uint32_t)kSmemMaskMats ? smem_masks[mat * 16u + (bit >> 5)] : __ldg(&g_masks[mat * 16u + (bit >> 5)]);
+#else
+        return __ldg(&g_masks[mat * 16u + (bit >> 5)]);
+#endif
     }
 };
 
@@ -475,7 +486,9 @@ constexpr int kWalkGap = UVT_WALK_GAP;          // trips between the end of a pr
 constexpr int kWalkBackoffShift = UVT_WALK_BACKOFF_SHIFT;  // ... after a failed walk: max_steps >> this (24 of 192 trips, 6 of 48)
 
 // Must be called by ALL 32 lanes of a warp (it uses full-mask warp reductions); `active` = this lane has a ray.
-template <int COUNT, bool DENSE>
+// SUN: the direction is camera.glsl's SUN_DIR (the shadow pass): the precomputed sun clearance (sun4) seals the ray at the
+// first lookup above it, and the column-tops walk is not needed.
+template <int COUNT, bool DENSE, bool SUN>
 __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool active, float ox, float oy, float oz, float dx, float dy, float dz,
                                                int max_steps, int bound, Hit &out, TripCounts &tc) {
     if (dx == 0.0f) dx = 0.001f;
@@ -544,7 +557,16 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
             if (simple && lim0 < max_steps) {  // (a run that reaches the cap seals the ray: general code)
                 limit = lim0;
                 slow = false;
-                walk = trip >= walk_at;
+                if (SUN) {  // within < 8: the state's block is g >> 3, its column group g >> 5
+                    const int row = gy >> 3;
+                    if (row > (int)__ldg(&w.sun4[((uint32_t)gx >> 5) + (udim >> 2) * ((uint32_t)gz >> 5)]) && row <= w.sun_row_max) {
+                        out.trips = (uint32_t)max_steps;  // sealed: iteration-cap miss (map.glsl:167)
+                        out.px = out.py = out.pz = 0xFFFFFFFFu;
+                        limit = kDead;
+                    }
+                } else {
+                    walk = trip >= walk_at;
+                }
 #ifndef UVT_ROUND_STATS
                 if (COUNT == 2) tc.t_in++;
 #endif
@@ -610,9 +632,17 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
                 out.px = px; out.py = py; out.pz = pz;
                 if (COUNT == 1) n_free = 0;  // exact reference counters need every lookup
                 limit = max(limit, trip + 1 + n_free);  // an earlier guarantee stays valid
-                const bool seal = COUNT != 1 && mat == 0u && limit >= max_steps;
+                bool seal = COUNT != 1 && mat == 0u && limit >= max_steps;
                 limit = min(limit, max_steps);
-                walk = mat == 0u && !seal && trip >= walk_at;
+                if (SUN && COUNT != 1) {  // the state's sub-voxel is `pos` (within >= 0), so its block is pos >> 3
+                    const uint32_t qd = (uint32_t)w.dim >> 2;
+                    if (mat == 0u && (px >> 5) < qd && (pz >> 5) < qd) {
+                        const int row = (int)(py >> 3);
+                        seal = seal || (row > (int)__ldg(&w.sun4[(px >> 5) + qd * (pz >> 5)]) && row <= w.sun_row_max);
+                    }
+                } else {
+                    walk = mat == 0u && !seal && trip >= walk_at;
+                }
                 if (seal) {
                     // sealed: nothing but empty in-map blocks until the iteration cap (map.glsl:167)
                     out.trips = (uint32_t)max_steps;
@@ -660,7 +690,7 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
         }
 
         // ---- column-tops walk: many free trips at once, or the seal (sealed rays, above) ----------
-        if (COUNT != 1 && walk) {
+        if (COUNT != 1 && !SUN && walk) {
             const int n_rem = max_steps - trip - 1;
             const int n = line_free_trips(w.clear4, w.clear16, w.clear64, w.dim, w.y_clear, ((float)gx + wx) * 0.125f, ((float)gy + wy) * 0.125f,
                                           ((float)gz + wz) * 0.125f, dx, dy, dz, invx, invy, invz, n_rem);
@@ -713,10 +743,10 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
 // dispatch: the compact world takes the fast path
 // COUNT: 0 none, 1 exact reference counters (t_in, t_chunk, t_block), 2 fast-path statistics (t_in = lookups performed)
 // Must be called by all 32 lanes of a warp; lanes without a ray pass active = false.
-template <class World, int COUNT>
+template <class World, int COUNT, bool SUN = false>
 __device__ __forceinline__ void trace(const World &w, bool active, float ox, float oy, float oz, float dx, float dy, float dz,
                                       int max_steps, int bound, Hit &out, TripCounts &tc) {
-    if constexpr (kIsCompact<World>) trace_map_fast<COUNT, std::is_same<World, WorldDense>::value>(w, active, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
+    if constexpr (kIsCompact<World>) trace_map_fast<COUNT, std::is_same<World, WorldDense>::value, SUN>(w, active, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
     else if (active) {
         trace_map<World, COUNT == 1>(w, ox, oy, oz, dx, dy, dz, max_steps, bound, out, tc);
         if (COUNT == 2) tc.t_in = tc.t_chunk = tc.t_block = 0;

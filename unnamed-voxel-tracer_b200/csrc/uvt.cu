@@ -62,6 +62,8 @@ struct uvt_ctx {
     bool incremental_ok = false;        // the last full commit left everything uvt_world_commit_region needs
     int32_t y_clear = 0;            // max occupied block y + 1 (every block at or above is empty)
     uint16_t *d_clear4 = nullptr;   // [(dim/4)^2] dilated column-group tops for sky_sealed()
+    uint16_t *d_sun4 = nullptr;     // [(dim/4)^2] sun clearance of the shadow pass (sun_clear_kernel), built for sun_steps trips
+    uint32_t sun_steps = 0;
     uint16_t *d_clear16 = nullptr;  // [ceil(dim/16)^2] their maxima over 16x16-block groups
     uint16_t *d_clear64 = nullptr;  // [ceil(dim/64)^2] ... over 64x64-block groups
     uint8_t *d_dense = nullptr;     // [dim^3] dense block grid (nullptr: not built — too large or disabled)
@@ -278,6 +280,9 @@ WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     a.w.dim = (int32_t)c->dim;
     a.w.clear4 = c->d_clear4;
     a.w.clear16 = c->d_clear16;
+    a.w.sun4 = c->d_sun4;
+    // the ray climbs at most (steps + 5) * u / (2 s + u) blocks; two blocks of slack under the top face
+    a.w.sun_row_max = (int32_t)c->dim - 3 - (int32_t)std::ceil((double)(c->sun_steps + 5) * UVT_SUN_Y / (2.0 * UVT_SUN_X + UVT_SUN_Y));
     a.w.clear64 = c->d_clear64;
     a.w.dense = c->d_dense;
     a.w.bricks8 = c->d_bricks8;
@@ -401,8 +406,18 @@ int launch_primary(uvt_ctx *c) {
     return check_launch(c, "primary_kernel");
 }
 
+// the sun clearance must cover the shadow step cap in force (it is built at commit time for the cap of that moment)
+void ensure_sun(uvt_ctx *c) {
+    if (!use_compact(c) || c->params.shadow_max_steps <= c->sun_steps) return;
+    const int d4 = (int)(c->dim / 4);
+    c->sun_steps = c->params.shadow_max_steps;
+    sun_clear_kernel<<<(d4 * d4 + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, c->d_sun4, d4, (int)c->sun_steps);
+    c->launches++;
+}
+
 template <int COUNT>
 int launch_secondary(uvt_ctx *c) {
+    ensure_sun(c);
     const ViewDev v = make_view(c, c->params.shadow_max_steps);
     const GBufDev g = make_gbuf(c);
     const dim3 grid = trace_grid(c);
@@ -448,7 +463,9 @@ int finish_tops(uvt_ctx *c, unsigned int *d_max) {
     const int d4 = (int)(c->dim / 4), d16 = (d4 + 3) / 4, d64 = (d16 + 3) / 4;
     coarse_clear_kernel<<<(d16 * d16 + 127) / 128, 128, 0, c->stream>>>(c->d_clear4, c->d_clear16, d4);
     coarse_clear_kernel<<<(d64 * d64 + 127) / 128, 128, 0, c->stream>>>(c->d_clear16, c->d_clear64, d16);
-    c->launches += 2;
+    c->sun_steps = std::max<uint32_t>(c->params.shadow_max_steps, 1u);
+    sun_clear_kernel<<<(d4 * d4 + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, c->d_sun4, d4, (int)c->sun_steps);
+    c->launches += 3;
     UVT_CUDA(c, cudaMemsetAsync(d_max, 0, 4, c->stream));
     max_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, nq, d_max);
     c->launches += 2;
@@ -660,7 +677,7 @@ void uvt_destroy(uvt_ctx *c) {
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
     cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
     cudaFree(c->d_rowmask); cudaFree(c->d_brick_chunk); cudaFree(c->d_tops32); cudaFree(c->d_scratch);
-    cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]); cudaFree(c->d_clear64); cudaFree(c->d_clear16);
+    cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]); cudaFree(c->d_clear64); cudaFree(c->d_clear16); cudaFree(c->d_sun4);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
     cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame);
     for (int i = 0; i < 4; ++i)
@@ -758,8 +775,8 @@ int uvt_pipeline_dispatch(uvt_pipeline *p, uint32_t gx, uint32_t gy, uint32_t gz
 static int reset_world(uvt_ctx *c, uint32_t dim) {
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
-    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32); cudaFree(c->d_clear64); cudaFree(c->d_clear16);
-    c->d_clear64 = c->d_clear16 = nullptr;
+    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32); cudaFree(c->d_clear64); cudaFree(c->d_clear16); cudaFree(c->d_sun4);
+    c->d_clear64 = c->d_clear16 = c->d_sun4 = nullptr;
     cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]);
     c->d_field = c->d_field_tmp[0] = c->d_field_tmp[1] = nullptr;
     c->d_dense = nullptr;
@@ -782,6 +799,7 @@ static int reset_world(uvt_ctx *c, uint32_t dim) {
     UVT_CUDA(c, cudaMalloc(&c->d_chunks2, (size_t)(c->cd + 1) * (c->cd + 1) * (c->cd + 1) * 4));
     UVT_CUDA(c, cudaMalloc(&c->d_clear4, (size_t)(dim / 4) * (dim / 4) * 2));
     UVT_CUDA(c, cudaMalloc(&c->d_clear16, (size_t)((dim + 15) / 16) * ((dim + 15) / 16) * 2));
+    UVT_CUDA(c, cudaMalloc(&c->d_sun4, (size_t)(dim / 4) * (dim / 4) * 2));
     UVT_CUDA(c, cudaMalloc(&c->d_clear64, (size_t)((dim + 63) / 64) * ((dim + 63) / 64) * 2));
     return UVT_OK;
 }
@@ -1261,6 +1279,7 @@ int uvt_dispatch_frame(uvt_ctx *c) {
     const bool batch = c->layers > 1;
     const uint32_t ss = c->params.shadow_max_steps;
     const FrameTarget ft = make_target(c);
+    ensure_sun(c);
     if (use_dense(c)) {
         if (batch) frame_kernel<WorldDense, true, true><<<grid, kThreads, 0, c->stream>>>(world_dense(c), cams, c->cam0, v, ss, g, ft);
         else frame_kernel<WorldDense, true, false><<<grid, kThreads, 0, c->stream>>>(world_dense(c), cams, c->cam0, v, ss, g, ft);
