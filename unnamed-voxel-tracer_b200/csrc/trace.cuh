@@ -475,15 +475,22 @@ __device__ __forceinline__ void dda_step_last(int &gx, int &gy, int &gz, float &
 // Rays with non-finite reciprocals or origins beyond 2^20 sub-voxels take the generic path,
 // whose corner-case behaviour (NaN ordering, saturation) is the specification.
 constexpr int kDead = 0x40000000;    // `limit` of a lane without a live ray
+#ifndef UVT_SHORT_LOOKUP
+#define UVT_SHORT_LOOKUP 1
+#endif
 #ifndef UVT_WALK_GAP
-#define UVT_WALK_GAP 8
+#define UVT_WALK_GAP 16
 #endif
 #ifndef UVT_WALK_BACKOFF_SHIFT
-#define UVT_WALK_BACKOFF_SHIFT 3
+#define UVT_WALK_BACKOFF_SHIFT 2
 #endif
+#ifndef UVT_WALK_MIN_CLEAR
+#define UVT_WALK_MIN_CLEAR 1
+#endif
+constexpr int kWalkMinClear = UVT_WALK_MIN_CLEAR;  // walk only when the block clearance of the lookup grants at least this many free trips
 constexpr int kWalkUseful = 4;                  // a walk that proves fewer free trips than this counts as failed
 constexpr int kWalkGap = UVT_WALK_GAP;          // trips between the end of a proven run and the lane's next walk
-constexpr int kWalkBackoffShift = UVT_WALK_BACKOFF_SHIFT;  // ... after a failed walk: max_steps >> this (24 of 192 trips, 6 of 48)
+constexpr int kWalkBackoffShift = UVT_WALK_BACKOFF_SHIFT;  // ... after a failed walk: max_steps >> this (48 of 192 trips)
 
 // Must be called by ALL 32 lanes of a warp (it uses full-mask warp reductions); `active` = this lane has a ray.
 // SUN: the direction is camera.glsl's SUN_DIR (the shadow pass): the precomputed sun clearance (sun4) seals the ray at the
@@ -544,7 +551,7 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
         // its clearance from the new position, which keeps the lanes' lookups aligned (fewer rounds).
         bool slow = limit < kDead;
         bool walk = false;  // this round's lookup found an empty block and the lane is due for a column-tops walk
-        if (DENSE && COUNT != 1 && slow) {
+        if (UVT_SHORT_LOOKUP && DENSE && COUNT != 1 && slow) {
             // the common lookup, kept short: a block step (no round-up carry) inside the map that finds an empty block and
             // does not seal the ray.  Anything else falls through to the general code below, which redoes the lookup.
             const uint32_t gmax = max(max((uint32_t)gx, (uint32_t)gy), (uint32_t)gz);
@@ -565,7 +572,7 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
                         limit = kDead;
                     }
                 } else {
-                    walk = trip >= walk_at;
+                    walk = trip >= walk_at && (int)code - (int)kMatLimit >= kWalkMinClear;
                 }
 #ifndef UVT_ROUND_STATS
                 if (COUNT == 2) tc.t_in++;
@@ -641,7 +648,7 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
                         seal = seal || (row > (int)__ldg(&w.sun4[(px >> 5) + qd * (pz >> 5)]) && row <= w.sun_row_max);
                     }
                 } else {
-                    walk = mat == 0u && !seal && trip >= walk_at;
+                    walk = mat == 0u && !seal && trip >= walk_at && n_free >= kWalkMinClear;
                 }
                 if (seal) {
                     // sealed: nothing but empty in-map blocks until the iteration cap (map.glsl:167)
