@@ -254,6 +254,21 @@ uint64_t uvt_launch_count(uvt_ctx *ctx);
 int  uvt_measure_l2_read_gbps(uvt_ctx *ctx, size_t bytes, int repeats, float *gbps);
 int  uvt_measure_hbm_copy_gbps(uvt_ctx *ctx, size_t bytes, int repeats, float *gbps);
 
+/* ---- NCCL band exchange ("finished tiles are gathered to the presenting rank with NCCL over NVLink") ----
+ * One ctx per rank (one process per GPU, or several ctxs in one process), partitioned with uvt_set_partition(band,
+ * n_ranks, rank).  uvt_nccl_unique_id() is called once (rank 0) and its 128 bytes handed to every rank by the host's own
+ * means; uvt_nccl_init() is collective.  uvt_dispatch_frame_nccl() renders the rank's bands in `n_groups` band groups and
+ * exchanges each finished group with grouped ncclSend / ncclRecv on a second stream while the next group is traversed:
+ * rank 0 receives every band straight at its rows of `full_frame` (device memory, W*H*4 bytes; NULL on the other ranks)
+ * and shades its own bands into it, so the assembled frame needs no reassembly pass.  Stream-ordered like every dispatch:
+ * the frame is complete on the ctx stream when the call's work is.  The library binds libnccl.so.2 at run time (in a
+ * torchrun process: the copy torch loaded); without it these calls fail with a message, nothing else is affected.
+ * The peer-to-peer band stores (uvt_shared_frame_*, uvt_group) remain the faster default; this is the NCCL variant. */
+int  uvt_nccl_unique_id(unsigned char id_out[128]);
+int  uvt_nccl_init(uvt_ctx *ctx, const unsigned char id[128], int n_ranks, int rank);
+int  uvt_nccl_shutdown(uvt_ctx *ctx);
+int  uvt_dispatch_frame_nccl(uvt_ctx *ctx, void *full_frame, uint32_t n_groups);
+
 /* ---- several GPUs in ONE process (the reference is a single-process game, src/game.zig) ----------
  * A group owns one ctx per device.  World and atlas are replicated from one pinned staging; the frame is cut into
  * interleaved 32-row bands (member i renders bands i, i+n, ...) and every member's kernels store their finished

@@ -90,6 +90,10 @@ SIGNATURES = {
     "uvt_readback_bands_async": (c_int, [c_p, c_p, c_size]),
     "uvt_host_register": (c_int, [c_p, c_p, c_size]),
     "uvt_host_unregister": (c_int, [c_p, c_p]),
+    "uvt_nccl_unique_id": (c_int, [c_p]),
+    "uvt_nccl_init": (c_int, [c_p, c_p, c_int, c_int]),
+    "uvt_nccl_shutdown": (c_int, [c_p]),
+    "uvt_dispatch_frame_nccl": (c_int, [c_p, c_p, c_u32]),
     "uvt_device_ptr": (c_int, [c_p, c_int, P(c_p)]),
     "uvt_bind_frame_target": (c_int, [c_p, c_p, c_u32, c_u32]),
     "uvt_deinterleave": (c_int, [c_p, c_p, c_p, c_u32]),

@@ -23,6 +23,7 @@ struct CamDev {
 struct ViewDev {
     uint32_t W, H;          // full frame
     uint32_t local_rows;    // rows stored by this ctx
+    uint32_t row0;          // first local row of this launch (band groups of uvt_dispatch_frame_nccl; 0 otherwise)
     uint32_t band_rows, n_parts, part;
     uint32_t map_dim;
     uint32_t max_steps;
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) primary_kernel(World
     }
     uint32_t x, ly, y;
     tile_pixel(x, ly);
+    ly += v.row0;
     const bool valid = v.global_row(ly, y) && x < v.W;
     const CamDev &cam = BATCH ? cams[blockIdx.z] : cam0;  // single camera: straight from the parameter bank
 
@@ -328,6 +330,7 @@ __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) secondary_kernel(Wor
     }
     uint32_t x, ly, y;
     tile_pixel(x, ly);
+    ly += v.row0;
     const bool valid = v.global_row(ly, y) && x < v.W;
     TripCounts tc = {0, 0, 0};
     uint32_t traced = 0, early = 0, hit = 0;
@@ -387,7 +390,7 @@ struct FrameTarget {
 
 __global__ void __launch_bounds__(256) shade_kernel(ViewDev v, GBufDev gb, FrameTarget ft) {
     const uint32_t x = blockIdx.x * 64u + (threadIdx.x & 63u);
-    const uint32_t ly = blockIdx.y * 4u + (threadIdx.x >> 6);
+    const uint32_t ly = v.row0 + blockIdx.y * 4u + (threadIdx.x >> 6);
     uint32_t y;
     if (!v.global_row(ly, y) || x >= v.W) return;
     const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;

@@ -7,6 +7,8 @@
 #include "uvt.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is bound at run time (dlopen), see NcclApi
 
 #include <algorithm>
 #include <cmath>
@@ -119,6 +121,13 @@ struct uvt_ctx {
     bool ev_valid[4] = {false, false, false, false};
     uint32_t *d_sink = nullptr;
     std::vector<void *> pinned;  // live uvt_alloc_pinned allocations
+
+    // ---- NCCL band exchange (uvt_nccl_init / uvt_dispatch_frame_nccl)
+    ncclComm_t nccl = nullptr;
+    int nccl_ranks = 0, nccl_rank = -1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t group_done[8] = {};   // band group g shaded (compute stream -> exchange stream)
+    cudaEvent_t exchange_done = nullptr;
 };
 
 struct uvt_pipeline {
@@ -300,6 +309,7 @@ ViewDev make_view(const uvt_ctx *c, uint32_t max_steps) {
     ViewDev v;
     v.W = c->W; v.H = c->H;
     v.local_rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
+    v.row0 = 0;
     v.band_rows = c->band_rows; v.n_parts = c->n_parts; v.part = c->part;
     v.map_dim = c->dim;
     v.max_steps = max_steps;
@@ -665,6 +675,7 @@ int uvt_create(const uvt_params *params, int device, uvt_ctx **out) {
 void uvt_destroy(uvt_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    uvt_nccl_shutdown(c);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < 2; ++i) {
@@ -1632,6 +1643,196 @@ int uvt_measure_hbm_copy_gbps(uvt_ctx *c, size_t bytes, int repeats, float *gbps
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "copy_kernel: %s", cudaGetErrorString(e));
     *gbps = (float)(2.0 * (double)bytes * repeats / (ms * 1e-3) / 1e9);
+    return UVT_OK;
+}
+
+}  // extern "C"
+
+// ---- NCCL band exchange ---------------------------------------------------------------
+// The frame is cut into interleaved bands (uvt_set_partition); with NCCL every non-presenting rank SENDS its finished
+// bands and rank 0 RECEIVES each of them straight at its place in the full frame (a band is a contiguous run of
+// band_rows * W pixels there), so no reassembly pass is needed.  NCCL has no gather: it is grouped ncclSend / ncclRecv.
+// The rank's bands are rendered in band GROUPS; the exchange of group g runs on a second stream while group g + 1 is
+// traversed.  libnccl is bound at run time: in a torchrun process that is the copy torch already loaded.
+namespace {
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+NcclApi *nccl_api() {
+    static NcclApi api;
+    if (api.lib || !api.error.empty()) return &api;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+        api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) {
+        api.error = std::string("libnccl.so.2 cannot be loaded: ") + dlerror();
+        return &api;
+    }
+#define UVT_NCCL_SYM(field, sym)                                                        \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, sym));              \
+    if (!api.field && api.error.empty()) api.error = std::string("libnccl lacks ") + sym;
+    UVT_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    UVT_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    UVT_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    UVT_NCCL_SYM(GroupStart, "ncclGroupStart")
+    UVT_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    UVT_NCCL_SYM(Send, "ncclSend")
+    UVT_NCCL_SYM(Recv, "ncclRecv")
+    UVT_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef UVT_NCCL_SYM
+    return &api;
+}
+
+#define UVT_NCCL(ctx, expr)                                                                                   \
+    do {                                                                                                      \
+        ncclResult_t r_ = (expr);                                                                             \
+        if (r_ != ncclSuccess) return set_error((ctx), UVT_ERR_CUDA, "%s: %s", #expr, nccl_api()->GetErrorString(r_)); \
+    } while (0)
+
+// rows [row0, row0 + nrows) of the ctx's local storage through the three passes of the frame (tile scheduler)
+int launch_rows(uvt_ctx *c, uint32_t row0, uint32_t nrows) {
+    ViewDev v = make_view(c, c->params.primary_max_steps);
+    v.row0 = row0;
+    const GBufDev g = make_gbuf(c);
+    const dim3 grid((c->W + kTileW - 1) / kTileW, (nrows + kTileH - 1) / kTileH, 1);
+    if (use_dense(c)) launch_primary_world<WorldDense, 0>(c, world_dense(c), v, g, grid);
+    else if (use_compact(c)) launch_primary_world<WorldCompact, 0>(c, world_compact(c), v, g, grid);
+    else launch_primary_world<WorldRef, 0>(c, world_ref(c), v, g, grid);
+    int rc = check_launch(c, "primary_kernel");
+    if (rc != UVT_OK) return rc;
+    v.max_steps = c->params.shadow_max_steps;
+    if (use_dense(c)) secondary_kernel<WorldDense, 0><<<grid, kThreads, 0, c->stream>>>(world_dense(c), v, g, c->d_counters);
+    else if (use_compact(c)) secondary_kernel<WorldCompact, 0><<<grid, kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
+    else secondary_kernel<WorldRef, 0><<<grid, kThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
+    rc = check_launch(c, "secondary_kernel");
+    if (rc != UVT_OK) return rc;
+    shade_kernel<<<dim3((c->W + 63) / 64, (nrows + 3) / 4, 1), 256, 0, c->stream>>>(v, g, make_target(c));
+    return check_launch(c, "shade_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+int uvt_nccl_unique_id(unsigned char id_out[128]) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    NcclApi *api = nccl_api();
+    if (!id_out) return UVT_ERR_INVALID;
+    if (!api->error.empty()) return set_error(nullptr, UVT_ERR_INVALID, "%s", api->error.c_str());
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) return set_error(nullptr, UVT_ERR_CUDA, "ncclGetUniqueId: %s", api->GetErrorString(r));
+    std::memcpy(id_out, &id, 128);
+    return UVT_OK;
+}
+
+int uvt_nccl_init(uvt_ctx *c, const unsigned char id[128], int n_ranks, int rank) {
+    if (!c || !id) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    NcclApi *api = nccl_api();
+    UVT_REQUIRE(c, api->error.empty(), api->error.c_str());
+    UVT_REQUIRE(c, n_ranks >= 1 && rank >= 0 && rank < n_ranks, "rank out of range");
+    UVT_REQUIRE(c, !c->nccl, "uvt_nccl_init called twice (uvt_nccl_shutdown first)");
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, 128);
+    UVT_NCCL(c, api->CommInitRank(&c->nccl, n_ranks, uid, rank));
+    c->nccl_ranks = n_ranks;
+    c->nccl_rank = rank;
+    {   // the exchange kernels must not queue behind the CTAs of the next band group: highest stream priority
+        int lo = 0, hi = 0;
+        UVT_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        UVT_CUDA(c, cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+    }
+    for (auto &e : c->group_done) UVT_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    UVT_CUDA(c, cudaEventCreateWithFlags(&c->exchange_done, cudaEventDisableTiming));
+    return UVT_OK;
+}
+
+int uvt_nccl_shutdown(uvt_ctx *c) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    if (!c->nccl) return UVT_OK;
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->comm_stream);
+    nccl_api()->CommDestroy(c->nccl);
+    c->nccl = nullptr;
+    cudaStreamDestroy(c->comm_stream);
+    c->comm_stream = nullptr;
+    for (auto &e : c->group_done) { cudaEventDestroy(e); e = nullptr; }
+    cudaEventDestroy(c->exchange_done);
+    c->exchange_done = nullptr;
+    return UVT_OK;
+}
+
+int uvt_dispatch_frame_nccl(uvt_ctx *c, void *full_frame, uint32_t n_groups) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    NcclApi *api = nccl_api();
+    UVT_REQUIRE(c, c->nccl, "no NCCL communicator (uvt_nccl_init first)");
+    UVT_REQUIRE(c, c->n_parts == (uint32_t)c->nccl_ranks && c->part == (uint32_t)c->nccl_rank, "uvt_set_partition(band, n_ranks, rank) must match the communicator");
+    UVT_REQUIRE(c, c->layers == 1, "batched poses are not tiled");
+    UVT_REQUIRE(c, n_groups >= 1 && n_groups <= 8, "1..8 band groups");
+    UVT_REQUIRE(c, c->nccl_rank != 0 || full_frame, "the presenting rank passes the W x H frame to assemble");
+    int rc = pre_dispatch(c);
+    if (rc != UVT_OK) return rc;
+    ensure_sun(c);
+    const uint32_t band = c->band_rows, n = c->n_parts, H = c->H;
+    const size_t band_px = (size_t)band * c->W;
+    const uint32_t n_bands = (H + band - 1) / band;
+    auto local_bands = [&](uint32_t part) { return part < n_bands ? (n_bands - part + n - 1) / n : 0u; };  // bands part, part + n, ...
+    const uint32_t mine = local_bands(c->part);
+    const uint32_t most = local_bands(0);                      // the largest part: every rank walks the same group boundaries
+    const uint32_t per_group = (most + n_groups - 1) / n_groups;
+    // the presenting rank's own pixels go straight to their place; the others shade into their compact band buffer
+    uint32_t *saved_target = c->frame_target;
+    const bool saved_global = c->frame_target_global_rows;
+    if (c->nccl_rank == 0) { c->frame_target = (uint32_t *)full_frame; c->frame_target_global_rows = true; }
+    else { c->frame_target = nullptr; c->frame_target_global_rows = false; }
+    PassTimer t(c, 3);
+    for (uint32_t g = 0; g < n_groups && rc == UVT_OK; ++g) {
+        const uint32_t lb0 = g * per_group, lb1 = std::min((g + 1) * per_group, most);
+        if (lb0 >= lb1) break;
+        if (lb0 < mine) rc = launch_rows(c, lb0 * band, (std::min(lb1, mine) - lb0) * band);
+        if (rc != UVT_OK) break;
+        if (n == 1) continue;
+        UVT_CUDA(c, cudaEventRecord(c->group_done[g], c->stream));
+        UVT_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->group_done[g], 0));
+        UVT_NCCL(c, api->GroupStart());
+        if (c->nccl_rank == 0) {
+            for (uint32_t p = 1; p < n; ++p)
+                for (uint32_t lb = lb0; lb < std::min(lb1, local_bands(p)); ++lb) {
+                    const uint32_t gb = lb * n + p;  // global band
+                    const size_t px = (size_t)std::min(band, H - gb * band) * c->W;
+                    UVT_NCCL(c, api->Recv((uint32_t *)full_frame + (size_t)gb * band_px, px, ncclUint32, (int)p, c->nccl, c->comm_stream));
+                }
+        } else {
+            for (uint32_t lb = lb0; lb < std::min(lb1, mine); ++lb) {
+                const uint32_t gb = lb * n + c->part;
+                const size_t px = (size_t)std::min(band, H - gb * band) * c->W;
+                UVT_NCCL(c, api->Send(c->d_frame + (size_t)lb * band_px, px, ncclUint32, 0, c->nccl, c->comm_stream));
+            }
+        }
+        UVT_NCCL(c, api->GroupEnd());
+    }
+    c->frame_target = saved_target;
+    c->frame_target_global_rows = saved_global;
+    if (rc != UVT_OK) return rc;
+    if (n > 1) {  // the frame is complete on the ctx stream once the last exchange has landed
+        UVT_CUDA(c, cudaEventRecord(c->exchange_done, c->comm_stream));
+        UVT_CUDA(c, cudaStreamWaitEvent(c->stream, c->exchange_done, 0));
+    }
     return UVT_OK;
 }
 

@@ -244,6 +244,26 @@ class Context:
         kind, _, _ = self._KINDS[name]
         self.check(self.L.uvt_readback_async(self.handle, kind, pinned.ctypes.data, pinned.nbytes))
 
+    @staticmethod
+    def nccl_unique_id():
+        """128-byte NCCL unique id (rank 0 creates it, the host hands it to every rank)."""
+        buf = (ctypes.c_ubyte * 128)()
+        rc = N.load().uvt_nccl_unique_id(buf)
+        if rc != N.UVT_OK:
+            raise UvtError(rc, N.load().uvt_last_error(None).decode())
+        return bytes(buf)
+
+    def nccl_init(self, unique_id, n_ranks, rank):
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(unique_id)
+        self.check(self.L.uvt_nccl_init(self.handle, buf, n_ranks, rank))
+
+    def nccl_shutdown(self):
+        self.check(self.L.uvt_nccl_shutdown(self.handle))
+
+    def dispatch_frame_nccl(self, full_frame_ptr=None, n_groups=4):
+        """The tiled frame with the NCCL band exchange overlapped with traversal (uvt_dispatch_frame_nccl)."""
+        self.check(self.L.uvt_dispatch_frame_nccl(self.handle, ctypes.c_void_p(full_frame_ptr or 0), n_groups))
+
     def readback_bands_async(self, host_frame):
         """This ctx's frame bands into their rows of a full W x H uint32 host frame (shared by all ranks of a tiled frame)."""
         self.check(self.L.uvt_readback_bands_async(self.handle, host_frame.ctypes.data, host_frame.nbytes))
