@@ -166,6 +166,14 @@ int  uvt_world_set_voxel(uvt_ctx *ctx, uint32_t x, uint32_t y, uint32_t z, uint3
  * view (brick bytes + far-empty chunk entries), out[2] column-group tops, out[3] = y_clear | n_materials << 32. */
 int  uvt_world_layout_checksum(uvt_ctx *ctx, uint64_t out[4]);
 
+/* procgen on the device (src/procgen.zig:6-70): the world the serial host procgen (uvt_procgen, uvt_host.h)
+ * writes — the same chunk table, brick numbering and brick words, byte for byte — generated by kernels.  Two steps because
+ * the brick count is only known after the plan: _plan returns it, the caller grows the staging the way GpuBlockAllocator
+ * would (uvt_world_grow), _fill writes device AND host staging.  uvt_world_commit(n_bricks) publishes it as usual.
+ * UVT_ERR_INVALID with "unsupported world" = more overlapping trees than the device path tracks: use the host procgen. */
+int  uvt_world_procgen_plan(uvt_ctx *ctx, float offset_x, float offset_y, size_t *n_bricks);
+int  uvt_world_procgen_fill(uvt_ctx *ctx);
+
 /* ---- atlas: VoxelModelAtlas → Texture.set_data_offset → glTextureSubImage3D
  *      (voxel.zig:88-131, texture.zig:70-72): RGBA8 sub-box, x fastest then y then z. */
 int  uvt_atlas_upload(uvt_ctx *ctx, uint32_t ox, uint32_t oy, uint32_t oz,

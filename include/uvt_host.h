@@ -59,6 +59,10 @@ int      uvt_brickmap_load(uvt_ctx *ctx, const char *path, uvt_brickmap **out);
 
 /* ---- procgen: src/procgen.zig:6-70 -------------------------------------------------- */
 int   uvt_procgen(uvt_brickmap *bm, uint32_t dim, float offset_x, float offset_y);
+/* The same world generated on the device (uvt_world_procgen_plan / _fill, include/uvt.h): bm must be attached to a ctx and
+ * empty.  UVT_ERR_INVALID when the device path does not apply (no ctx, a group, a non-empty map, an unsupported world):
+ * call uvt_procgen then. */
+int   uvt_procgen_device(uvt_brickmap *bm, uint32_t dim, float offset_x, float offset_y);
 /* FastNoiseLite-style OpenSimplex2 FBm with znoise FnlGenerator defaults (procgen.zig:7);
  * restated from the published algorithm, NOT byte-verified against the library. */
 float uvt_noise2_fbm(float x, float y);

@@ -1088,3 +1088,43 @@ def test_caller_owned_staging(uvt, oracle, world64, models):
         world = oracle.World(64, chunks.copy(), bigger[:n + 1].copy(), world64.oracle_world.atlas)
         assert_primary_parity(b, oracle.render(world, cam, 96, 64))
         assert not np.array_equal(a["hits"]["block"], b["hits"]["block"])
+
+
+# ---- procgen on the device ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,off", [(64, (0.0, 0.0)), (128, (0.0, 0.0)), (512, (0.0, 0.0)), (512, (1234.5, -77.25)), (1024, (300.0, 900.0)), (2048, (0.0, 0.0))])
+def test_device_procgen_equals_host_procgen(uvt, dim, off):
+    """uvt_procgen_device: the world of the serial host procgen (src/procgen.zig restated in csrc/host/world.cpp) byte for byte —
+    chunk table, brick numbering (first-touch order of the allocator), brick words, pool capacity — for several sizes and noise
+    offsets (other offsets move the hills, the water line crossings and the trees)."""
+    host = uvt.voxel.VoxelBrickmap.init(dim, 8, None)
+    uvt.procgen.procgen(dim, host, *off, device="host")
+    with uvt.Context(0, map_dim=dim) as ctx:
+        dev = uvt.voxel.VoxelBrickmap.init(dim, 8, ctx)
+        uvt.procgen.procgen(dim, dev, *off, device="device")
+        assert dev.n_bricks == host.n_bricks and dev.capacity == host.capacity
+        assert np.array_equal(dev.chunks(), host.chunks())
+        hb, db = host.bricks(), dev.bricks()
+        if not np.array_equal(db, hb):
+            bad = np.argwhere(db.reshape(-1, 512) != hb.reshape(-1, 512))
+            raise AssertionError(f"{len(bad)} brick words differ, first at brick/offset {bad[:5].tolist()}")
+        dev.bind(9)   # and it commits like any other world
+        assert ctx.effective_layout() == "compact"
+
+
+def test_device_procgen_is_the_default_for_a_fresh_map_on_a_ctx(uvt, oracle, models):
+    """procgen(..., device="auto"): device path for an empty map attached to a ctx, host path otherwise; same frame either way."""
+    cam = uvt.scenes.camera_k1(512)
+    frames = []
+    for mode in ("auto", "host"):
+        with uvt.Context(0) as ctx:
+            bm = uvt.voxel.VoxelBrickmap.init(512, 8, ctx)
+            uvt.procgen.procgen(512, bm, device=mode)
+            atlas = uvt.voxel.VoxelModelAtlas.init(ctx)
+            for m in models:
+                atlas.append_model(m)
+            bm.bind(9)
+            ctx.resize(320, 180)
+            ctx.set_camera(cam)
+            ctx.dispatch_frame()
+            frames.append(ctx.readback("frame").copy())
+    assert np.array_equal(frames[0], frames[1])

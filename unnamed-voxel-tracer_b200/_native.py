@@ -144,6 +144,9 @@ SIGNATURES = {
     "uvt_brickmap_save": (c_int, [c_p, ctypes.c_char_p]),
     "uvt_brickmap_load": (c_int, [c_p, ctypes.c_char_p, P(c_p)]),
     "uvt_procgen": (c_int, [c_p, c_u32, c_f, c_f]),
+    "uvt_procgen_device": (c_int, [c_p, c_u32, c_f, c_f]),
+    "uvt_world_procgen_plan": (c_int, [c_p, c_f, c_f, P(c_size)]),
+    "uvt_world_procgen_fill": (c_int, [c_p]),
     "uvt_noise2_fbm": (c_f, [c_f, c_f]),
     "uvt_procgen_height": (c_u32, [c_u32, c_u32, c_u32, c_f, c_f]),
     "uvt_vox_parse": (c_int, [c_p, c_size, P(c_p)]),

@@ -234,13 +234,6 @@ int uvt_brickmap_load(uvt_ctx *ctx, const char *path, uvt_brickmap **out) {
 
 // ---- procgen: src/procgen.zig:6-70 -----------------------------------------------------
 
-uint32_t uvt_procgen_height(uint32_t dim, uint32_t x, uint32_t z, float offset_x, float offset_y) {
-    // procgen.zig:23-24: noise2((offX + x)/10, (offY + z)/10); vh = u32(max(val * dim * 0.1, 0))
-    const float val = uvt_noise2_fbm((offset_x + (float)x) / 10.0f, (offset_y + (float)z) / 10.0f);
-    const float h = std::max(val * (float)dim * 0.1f, 0.0f);
-    return (uint32_t)h;
-}
-
 // place_tree: procgen.zig:55-70
 static int place_tree(uvt_lcg *lcg, uvt_brickmap *w, uint32_t x, uint32_t y, uint32_t z) {
     const uint32_t trunk_height = uvt_lcg_rand(lcg) % 4 + 4;
@@ -297,6 +290,29 @@ int uvt_procgen(uvt_brickmap *world, uint32_t dim, float offset_x, float offset_
             (void)uvt_lcg_rand(&lcg);
         }
     }
+    return UVT_OK;
+}
+
+// procgen on the device: the same world as uvt_procgen above, byte for byte, generated by kernels
+// (csrc/procgen.cuh).  The map must be attached to a ctx and empty.  The brick pool is grown exactly as
+// GpuBlockAllocator.alloc would have grown it (doubling from `dim` bricks), so capacity and dump are identical too.
+int uvt_procgen_device(uvt_brickmap *world, uint32_t dim, float offset_x, float offset_y) {
+    if (!world || dim != world->dim || !world->ctx || world->group || world->block_index != 0) return UVT_ERR_INVALID;
+    size_t n = 0;
+    int rc = uvt_world_procgen_plan(world->ctx, offset_x, offset_y, &n);
+    if (rc != UVT_OK) return rc;
+    while (world->max_block_index < n) {
+        const size_t new_cap = world->max_block_index * 2;
+        uint32_t *nb = nullptr;
+        rc = uvt_world_grow(world->ctx, new_cap, &nb);
+        if (rc != UVT_OK) return rc;
+        world->bricks = nb;
+        world->max_block_index = new_cap;
+    }
+    rc = uvt_world_procgen_fill(world->ctx);
+    if (rc != UVT_OK) return rc;
+    world->block_index = n;
+    world->dirty = world->dirty_all = true;
     return UVT_OK;
 }
 

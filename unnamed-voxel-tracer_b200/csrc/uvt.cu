@@ -21,8 +21,11 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "kernels.cuh"
 #include "pool.cuh"
+#include "procgen.cuh"
 
 using namespace uvt;
 
@@ -121,6 +124,16 @@ struct uvt_ctx {
     bool ev_valid[4] = {false, false, false, false};
     uint32_t *d_sink = nullptr;
     std::vector<void *> pinned;  // live uvt_alloc_pinned allocations
+
+    // ---- device procgen (uvt_world_procgen_plan / _fill): temporaries kept between the two calls
+    struct {
+        uint16_t *vh = nullptr;
+        uint32_t *seeds = nullptr, *deco = nullptr;
+        uvt::pg::Tree *trees = nullptr;
+        uint32_t n_trees = 0;
+        size_t n_bricks = 0;
+        bool planned = false;
+    } pgen;
 
     // ---- NCCL band exchange (uvt_nccl_init / uvt_dispatch_frame_nccl)
     ncclComm_t nccl = nullptr;
@@ -676,6 +689,7 @@ void uvt_destroy(uvt_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     uvt_nccl_shutdown(c);
+    cudaFree(c->pgen.vh); cudaFree(c->pgen.seeds); cudaFree(c->pgen.deco); cudaFree(c->pgen.trees);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < 2; ++i) {
@@ -1833,6 +1847,145 @@ int uvt_dispatch_frame_nccl(uvt_ctx *c, void *full_frame, uint32_t n_groups) {
         UVT_CUDA(c, cudaEventRecord(c->exchange_done, c->comm_stream));
         UVT_CUDA(c, cudaStreamWaitEvent(c->stream, c->exchange_done, 0));
     }
+    return UVT_OK;
+}
+
+}  // extern "C"
+
+// ---- procgen on the device (src/procgen.zig:6-70) --------------------------------------
+extern "C" {
+
+static void procgen_release(uvt_ctx *c) {
+    cudaFree(c->pgen.vh); cudaFree(c->pgen.seeds); cudaFree(c->pgen.deco); cudaFree(c->pgen.trees);
+    c->pgen.vh = nullptr; c->pgen.seeds = c->pgen.deco = nullptr; c->pgen.trees = nullptr;
+    c->pgen.planned = false;
+}
+
+int uvt_world_procgen_plan(uvt_ctx *c, float offset_x, float offset_y, size_t *n_bricks) {
+    if (!c || !n_bricks) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_REQUIRE(c, c->h_chunks && c->d_chunks, "no world allocated (uvt_world_alloc first)");
+    UVT_REQUIRE(c, c->dim >= 16, "procgen needs a map of at least 16 blocks (the y < 16 slab)");
+    namespace pg = uvt::pg;
+    procgen_release(c);
+    const uint32_t dim = c->dim, cd = c->cd;
+    const size_t n_col = (size_t)dim * dim, n_chunks = (size_t)cd * cd * cd;
+    const uint32_t max_trees = 1u << 16;
+
+    // LCG jump table and gradient table (host, tiny)
+    std::vector<uint2> jump(2 * (size_t)dim + 64);
+    jump[0] = make_uint2(1u, 0u);
+    for (size_t n = 1; n < jump.size(); ++n) jump[n] = make_uint2(jump[n - 1].x * pg::kLcgA, jump[n - 1].y * pg::kLcgA + pg::kLcgC);
+    float grad[256];
+    uvt_noise::build_grad_table(grad);
+
+    uint2 *d_jump = nullptr;
+    float *d_grad = nullptr;
+    ushort2 *d_blocked = nullptr;
+    uint8_t *d_nblocked = nullptr;
+    uint32_t *d_misc = nullptr;  // [0] n_trees [1] status [2] final seed [3] n_touched
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
+    uint32_t *d_idx = nullptr, *d_idx2 = nullptr;
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_jump); cudaFree(d_grad); cudaFree(d_blocked); cudaFree(d_nblocked); cudaFree(d_misc);
+        cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_tmp);
+    };
+#define UVT_PG(expr)                                                                                                    \
+    do {                                                                                                                \
+        cudaError_t e_ = (expr);                                                                                        \
+        if (e_ != cudaSuccess) {                                                                                        \
+            cleanup();                                                                                                  \
+            procgen_release(c);                                                                                         \
+            return set_error(c, e_ == cudaErrorMemoryAllocation ? UVT_ERR_OOM : UVT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+        }                                                                                                               \
+    } while (0)
+    UVT_PG(cudaMalloc(&c->pgen.vh, n_col * 2));
+    UVT_PG(cudaMalloc(&c->pgen.seeds, n_col * 4));
+    UVT_PG(cudaMalloc(&c->pgen.deco, n_col * 4));
+    UVT_PG(cudaMalloc(&c->pgen.trees, (size_t)max_trees * sizeof(pg::Tree)));
+    UVT_PG(cudaMalloc(&d_jump, jump.size() * sizeof(uint2)));
+    UVT_PG(cudaMalloc(&d_grad, sizeof grad));
+    UVT_PG(cudaMalloc(&d_blocked, (size_t)3 * dim * pg::kMaxRanges * sizeof(ushort2)));
+    UVT_PG(cudaMalloc(&d_nblocked, (size_t)3 * dim));
+    UVT_PG(cudaMalloc(&d_misc, 16));
+    UVT_PG(cudaMalloc(&d_keys, n_chunks * 8));
+    UVT_PG(cudaMalloc(&d_keys2, n_chunks * 8));
+    UVT_PG(cudaMalloc(&d_idx, n_chunks * 4));
+    UVT_PG(cudaMalloc(&d_idx2, n_chunks * 4));
+    UVT_PG(cudaMemcpyAsync(d_jump, jump.data(), jump.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    UVT_PG(cudaMemcpyAsync(d_grad, grad, sizeof grad, cudaMemcpyHostToDevice, c->stream));
+    UVT_PG(cudaMemsetAsync(c->pgen.deco, 0, n_col * 4, c->stream));
+    UVT_PG(cudaMemsetAsync(d_nblocked, 0, (size_t)3 * dim, c->stream));
+    UVT_PG(cudaMemsetAsync(d_misc, 0, 16, c->stream));
+    UVT_PG(cudaMemsetAsync(d_keys, 0xFF, n_chunks * 8, c->stream));
+    UVT_PG(cudaMemsetAsync(c->d_chunks, 0, n_chunks * 4, c->stream));
+
+    pg::heights_kernel<<<dim3((dim + 127) / 128, dim), 128, 0, c->stream>>>(d_grad, dim, offset_x, offset_y, c->pgen.vh);
+    pg::scan_kernel<<<1, 32, 0, c->stream>>>(c->pgen.vh, dim, d_jump, 0x46AE4Fu, c->pgen.seeds, c->pgen.deco, c->pgen.trees, max_trees, d_misc,
+                                             d_blocked, d_nblocked, d_misc + 1, d_misc + 2);
+    c->launches += 2;
+    uint32_t misc[4] = {0, 0, 0, 0};
+    UVT_PG(cudaMemcpyAsync(misc, d_misc, 16, cudaMemcpyDeviceToHost, c->stream));
+    UVT_PG(cudaStreamSynchronize(c->stream));
+    if (misc[1] != 0) {  // more tree ranges / trees than the device path keeps: the caller falls back to the serial host procgen
+        cleanup();
+        procgen_release(c);
+        return set_error(c, UVT_ERR_INVALID, "device procgen: unsupported world (status %u)", misc[1]);
+    }
+    c->pgen.n_trees = misc[0];
+
+    pg::touch_kernel<<<(cd * cd + 127) / 128, 128, 0, c->stream>>>(c->pgen.vh, c->pgen.deco, dim, d_keys);
+    if (c->pgen.n_trees) pg::tree_touch_kernel<<<(c->pgen.n_trees + 63) / 64, 64, 0, c->stream>>>(c->pgen.trees, c->pgen.n_trees, dim, d_keys, d_misc + 1);
+    pg::iota_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, c->stream>>>(d_idx, (uint32_t)n_chunks);
+    size_t tmp_bytes = 0;
+    UVT_PG(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_idx, d_idx2, (int)n_chunks, 0, 64, c->stream));
+    UVT_PG(cudaMalloc(&d_tmp, tmp_bytes));
+    UVT_PG(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_idx, d_idx2, (int)n_chunks, 0, 64, c->stream));
+    pg::slab_chunks_kernel<<<(2 * cd * cd + 255) / 256, 256, 0, c->stream>>>(c->d_chunks, cd);
+    pg::ranked_chunks_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, c->stream>>>(d_keys2, d_idx2, (uint32_t)n_chunks, 2 * cd * cd, c->d_chunks, d_misc + 3);
+    c->launches += 5;
+    UVT_PG(cudaMemcpyAsync(misc, d_misc, 16, cudaMemcpyDeviceToHost, c->stream));
+    UVT_PG(cudaStreamSynchronize(c->stream));
+    UVT_PG(cudaGetLastError());
+#undef UVT_PG
+    cleanup();
+    if (misc[1] != 0) {
+        procgen_release(c);
+        return set_error(c, UVT_ERR_INVALID, "device procgen: unsupported world (status %u)", misc[1]);
+    }
+    c->pgen.n_bricks = (size_t)2 * cd * cd + misc[3];
+    c->pgen.planned = true;
+    *n_bricks = c->pgen.n_bricks;
+    return UVT_OK;
+}
+
+int uvt_world_procgen_fill(uvt_ctx *c) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_REQUIRE(c, c->pgen.planned, "uvt_world_procgen_plan first");
+    UVT_REQUIRE(c, c->pgen.n_bricks <= c->h_capacity, "the staging holds fewer bricks than the world needs (uvt_world_grow first)");
+    namespace pg = uvt::pg;
+    const uint32_t dim = c->dim, cd = c->cd;
+    const size_t n = c->pgen.n_bricks, n_chunks = (size_t)cd * cd * cd;
+    if (n > c->d_brick_capacity) {
+        cudaFree(c->d_bricks);
+        c->d_bricks = nullptr;
+        c->d_brick_capacity = 0;
+        const size_t want = std::max(n, c->h_capacity);
+        UVT_CUDA(c, cudaMalloc(&c->d_bricks, want * 2048));
+        c->d_brick_capacity = want;
+    }
+    UVT_CUDA(c, cudaMemsetAsync(c->d_bricks, 0, n * 2048, c->stream));
+    pg::fill_kernel<<<dim3((dim + 63) / 64, dim), 64, 0, c->stream>>>(c->pgen.vh, c->pgen.seeds, c->pgen.deco, c->d_chunks, dim, c->d_bricks);
+    pg::tree_fill_kernel<<<1, 32, 0, c->stream>>>(c->pgen.trees, c->pgen.n_trees, c->pgen.vh, c->d_chunks, dim, c->d_bricks);
+    c->launches += 2;
+    // the host keeps the world too (VoxelBrickmap.get / is_walkable read the staging; edits go through it)
+    UVT_CUDA(c, cudaMemcpyAsync(c->h_chunks, c->d_chunks, n_chunks * 4, cudaMemcpyDeviceToHost, c->stream));
+    UVT_CUDA(c, cudaMemcpyAsync(c->h_bricks, c->d_bricks, n * 2048, cudaMemcpyDeviceToHost, c->stream));
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    UVT_CUDA(c, cudaGetLastError());
+    procgen_release(c);
     return UVT_OK;
 }
 
