@@ -301,8 +301,9 @@ int uvt_procgen_device(uvt_brickmap *world, uint32_t dim, float offset_x, float 
     size_t n = 0;
     int rc = uvt_world_procgen_plan(world->ctx, offset_x, offset_y, &n);
     if (rc != UVT_OK) return rc;
-    while (world->max_block_index < n) {
-        const size_t new_cap = world->max_block_index * 2;
+    size_t new_cap = world->max_block_index;
+    while (new_cap < n) new_cap *= 2;   // the capacity the doubling allocator ends at, reached in one step (the map is empty)
+    if (new_cap != world->max_block_index) {
         uint32_t *nb = nullptr;
         rc = uvt_world_grow(world->ctx, new_cap, &nb);
         if (rc != UVT_OK) return rc;

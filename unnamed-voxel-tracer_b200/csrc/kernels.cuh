@@ -496,6 +496,36 @@ __global__ void pick_kernel(WorldArgs<World> wa, CamDev cam, ViewDev v, uint8_t 
     store_hit(out_hit, 0, h, dist);
 }
 
+// ---- the distinct block words of the committed bricks (the material table of the compact layout) --------------
+// Open-addressed set in global memory; a world holds a few dozen distinct words, so almost every probe is a plain read of
+// an entry that is already there.  `overflow` is set when the set fills up (more words than the 8-bit layout can name anyway).
+constexpr uint32_t kWordSetSlots = 2048;
+__global__ void distinct_words_kernel(const uint32_t *__restrict__ bricks, size_t n_words, uint32_t *table, uint32_t *overflow) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4u;
+    uint32_t last = 0;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4u; i < n_words; i += stride) {
+        const uint4 wv = *reinterpret_cast<const uint4 *>(bricks + i);
+        const uint32_t wds[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t wd = wds[k];
+            if (wd == 0u || wd == last) continue;
+            last = wd;
+            uint32_t slot = (wd * 2654435761u) >> 21;
+            for (uint32_t probe = 0;; ++probe) {
+                const uint32_t v = *(volatile uint32_t *)&table[slot];
+                if (v == wd) break;
+                if (v == 0u) {
+                    const uint32_t old = atomicCAS(&table[slot], 0u, wd);
+                    if (old == 0u || old == wd) break;
+                }
+                if (probe >= kWordSetSlots) { *overflow = 1u; break; }
+                slot = (slot + 1u) & (kWordSetSlots - 1u);
+            }
+        }
+    }
+}
+
 // ---- world repack: reference u32 bricks -> 8-bit material bricks ---------------------------
 // mat_lut maps a block word to its material id through a small open-addressed table built on the host.
 __global__ void repack_bricks_kernel(const uint32_t *__restrict__ bricks, uint8_t *__restrict__ bricks8, size_t n_words,

@@ -43,107 +43,203 @@ __global__ void heights_kernel(const float *__restrict__ grad, uint32_t dim, flo
 }
 
 // n % d == 0 for odd d, without a division: n * d^-1 (mod 2^32) <= (2^32 - 1) / d
-__device__ __forceinline__ bool divisible(uint32_t n, uint32_t inv, uint32_t limit) { return n * inv <= limit; }
+__host__ __device__ __forceinline__ bool divisible(uint32_t n, uint32_t inv, uint32_t limit) { return n * inv <= limit; }
+constexpr uint32_t kInv5 = 0xCCCCCCCDu, kLim5 = 0xFFFFFFFFu / 5u;
+constexpr uint32_t kInv71 = 0xE327A977u, kLim71 = 0xFFFFFFFFu / 71u;     // 71 * 0xE327A977 == 1 (mod 2^32)
+constexpr uint32_t kInv105 = 0xD8FD8FD9u, kLim105 = 0xFFFFFFFFu / 105u;  // 420 = 4 * 105
 
-// ONE thread.  jump[n] = (A_n, C_n) with L^n(s) = A_n * s + C_n.  blocked[3][dim][kMaxRanges] / n_blocked[3][dim]: height ranges
-// of tree blocks over the columns of rows x, x + 1, x + 2 (a tree reaches two columns ahead).  status: 1 = range overflow.
-__global__ void scan_kernel(const uint16_t *__restrict__ vh, uint32_t dim, const uint2 *__restrict__ jump, uint32_t seed0,
-                            uint32_t *__restrict__ seeds, uint32_t *__restrict__ deco, Tree *__restrict__ trees, uint32_t max_trees,
+// L^k(s) = A[k] * s + C[k], k = 0..5
+struct LcgPow {
+    uint32_t A[6], C[6];
+    __host__ __device__ LcgPow() {
+        A[0] = 1u; C[0] = 0u;
+        for (int k = 1; k < 6; ++k) { A[k] = A[k - 1] * kLcgA; C[k] = C[k - 1] * kLcgA + kLcgC; }
+    }
+};
+
+// body draws of a column: one per block, one more for sand (h <= 15) or for the top layer (procgen.zig:26-33)
+__host__ __device__ __forceinline__ uint32_t body_draws(uint32_t h) { return h + (h < 16u ? h : 16u) + (h > 16u ? 1u : 0u); }
+
+// ---- the LCG scan -------------------------------------------------------------------------------------------------
+// One CTA, ONE lane carries the LCG state through the columns in the reference order; the other warps prepare, one tile
+// ahead, what does not depend on that state.  For a column of height h, with (Aj, Cj) the jump over its body draws:
+//   * h <= 16: no decoration, s' = L^(b+1)(s) (body + the trailing draw of procgen.zig:52);
+//   * h > 16:  r1 = L(sb) decides (r1 % 5 == 0) between 5 and 4 further draws (grass type, r2, r3, trailing) — the test and
+//     both outcomes are AFFINE in s with per-column constants: hit <=> M s + K <= (2^32 - 1) / 5, s' = Ah s + Ch or An s + Cn.
+//     That is the whole dependent chain of an ordinary column: 3 multiply-adds, a compare, a select.
+// Trees (r3 % 420 == 0) can only be planted for 5 < x, z < 500 and reach two columns further (procgen.zig:47, 55-70), so only
+// tiles that intersect [6, 501]^2 take the general per-column code (tree test, the `continue` of procgen.zig:37-38 against the
+// height ranges earlier trees occupy); W4 has 6 % of its columns there.
+constexpr int kScanTile = 256, kScanThreads = 128;
+
+struct ScanTile {
+    uint4 hit[kScanTile];   // m, k (hit <=> m s + k <= kLim5), ah, ch (s' after a hit)
+    uint4 miss[kScanTile];  // an, cn (s' after a miss; also r3 after a hit), a3, c3 (r3 after a miss)
+    uint32_t h[kScanTile];
+};
+
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(const uint16_t *__restrict__ vh, uint32_t dim, const uint2 *__restrict__ jump, uint32_t seed0,
+                            uint32_t *__restrict__ seeds, uint8_t *__restrict__ skipped, Tree *__restrict__ trees, uint32_t max_trees,
                             uint32_t *__restrict__ n_trees_out, ushort2 *__restrict__ blocked, uint8_t *__restrict__ n_blocked,
                             uint32_t *__restrict__ status, uint32_t *__restrict__ final_seed) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    constexpr uint32_t inv5 = 0xCCCCCCCDu, lim5 = 0xFFFFFFFFu / 5u;
-    constexpr uint32_t inv71 = 0xE327A977u, lim71 = 0xFFFFFFFFu / 71u;     // 71 * 0xE327A977 == 1 (mod 2^32)
-    constexpr uint32_t inv105 = 0xD8FD8FD9u, lim105 = 0xFFFFFFFFu / 105u;  // 420 = 4 * 105
-    // affine powers of the LCG step
-    uint32_t A[6], C[6];
-    A[0] = 1u; C[0] = 0u;
-    for (int k = 1; k < 6; ++k) { A[k] = A[k - 1] * kLcgA; C[k] = C[k - 1] * kLcgA + kLcgC; }
+    __shared__ ScanTile tiles[2];
+    const LcgPow P;
+    const uint32_t tiles_per_row = (dim + kScanTile - 1) / kScanTile, n_tiles = tiles_per_row * dim;
+    const uint32_t warp = threadIdx.x >> 5;
+
+    auto prepare = [&](uint32_t t, ScanTile &T, uint32_t first, uint32_t stride) {
+        const uint32_t x = t / tiles_per_row, z0 = (t % tiles_per_row) * kScanTile;
+        for (uint32_t q = first; q < (uint32_t)kScanTile; q += stride) {
+            if (z0 + q >= dim) {  // padding of the row's last tile: the identity
+                T.hit[q] = make_uint4(0u, 0xFFFFFFFFu, 1u, 0u);
+                T.miss[q] = make_uint4(1u, 0u, 1u, 0u);
+                T.h[q] = 0u;
+                continue;
+            }
+            const uint32_t h = vh[(size_t)x * dim + z0 + q];
+            const uint32_t b = body_draws(h);
+            T.h[q] = h;
+            if (h <= 16u) {  // never a hit; s' = body + the trailing draw
+                const uint2 j1 = __ldg(&jump[b + 1u]);
+                T.hit[q] = make_uint4(0u, 0xFFFFFFFFu, j1.x, j1.y);
+                T.miss[q] = make_uint4(j1.x, j1.y, 1u, 1u);  // (r3 = s + 1 is never tested: h <= 16 columns plant nothing)
+            } else {
+                const uint2 j = __ldg(&jump[b]);
+                T.hit[q] = make_uint4(P.A[1] * j.x * kInv5, (P.A[1] * j.y + P.C[1]) * kInv5, P.A[5] * j.x, P.A[5] * j.y + P.C[5]);
+                T.miss[q] = make_uint4(P.A[4] * j.x, P.A[4] * j.y + P.C[4], P.A[3] * j.x, P.A[3] * j.y + P.C[3]);
+            }
+        }
+    };
+
+    prepare(0, tiles[0], threadIdx.x, kScanThreads);
+    __syncthreads();
+
     uint32_t s = seed0, n_trees = 0;
-    int last_tree_x = -100;
-    bool row_dirty[3] = {false, false, false};  // n_blocked is zeroed by the caller
-    for (uint32_t x = 0; x < dim; ++x) {
-        {   // the row that enters the three-row window
-            const uint32_t r = (x + 2u) % 3u;
-            if (row_dirty[r]) {
-                for (uint32_t z = 0; z < dim; ++z) n_blocked[r * dim + z] = 0;
-                row_dirty[r] = false;
-            }
-        }
-        const bool near_tree = last_tree_x + 2 >= (int)x;
-        const uint16_t *row = vh + (size_t)x * dim;
-        for (uint32_t z0 = 0; z0 < dim; z0 += 4) {
-            // heights and jump entries of four columns first: their latency is off the LCG chain
-            const uint2 hh = *reinterpret_cast<const uint2 *>(row + z0);
-            const uint32_t h4[4] = {hh.x & 0xFFFFu, hh.x >> 16, hh.y & 0xFFFFu, hh.y >> 16};
-            uint2 j4[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t h = h4[k];
-                j4[k] = __ldg(&jump[h + min(h, 16u) + (h > 16u ? 1u : 0u)]);  // body draws: one per block, one more for sand (h <= 15) / the top layer
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t z = z0 + k, h = h4[k];
-                const size_t i = (size_t)x * dim + z;
-                seeds[i] = s;
-                const uint32_t sb = j4[k].x * s + j4[k].y;  // state after the column body
-                if (h <= 16u) {                             // no decoration: the trailing draw only (procgen.zig:52)
-                    s = sb * kLcgA + kLcgC;
-                    continue;
+    bool row_dirty[3] = {false, false, false};             // n_blocked is zeroed by the caller
+    uint32_t blk_lo[3] = {~0u, ~0u, ~0u}, blk_hi[3] = {0u, 0u, 0u};  // z range of the columns with tree ranges, per window row
+
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        if (warp != 0) {
+            if (t + 1 < n_tiles) prepare(t + 1, tiles[(t + 1) & 1], threadIdx.x - 32u, kScanThreads - 32u);
+        } else if (threadIdx.x == 0) {
+            const ScanTile &T = tiles[t & 1];
+            const uint32_t x = t / tiles_per_row, z0 = (t % tiles_per_row) * kScanTile;
+            const uint32_t nz = min((uint32_t)kScanTile, dim - z0);
+            uint32_t *out = seeds + (size_t)x * dim + z0;
+            if (z0 == 0) {  // the row that enters the three-row window of tree ranges
+                const uint32_t r = (x + 2u) % 3u;
+                if (row_dirty[r]) {
+                    for (uint32_t z = blk_lo[r]; z <= blk_hi[r]; ++z) n_blocked[r * dim + z] = 0;
+                    row_dirty[r] = false;
+                    blk_lo[r] = ~0u; blk_hi[r] = 0u;
                 }
-                if (near_tree || last_tree_x + 2 >= (int)x) {  // procgen.zig:37-38: something (a tree block) already at (x, vh, z)
-                    const uint32_t r = x % 3u;
-                    bool blk = false;
-                    for (uint32_t q = 0; q < n_blocked[r * dim + z]; ++q) {
-                        const ushort2 rg = blocked[((size_t)r * dim + z) * kMaxRanges + q];
-                        blk = blk || (h >= rg.x && h <= rg.y);
+            }
+            const bool general = x >= 6u && x <= 501u && z0 <= 501u && z0 + nz > 6u;
+            if (!general) {
+                // groups of four columns: the constants of the next group are fetched while this group's chain runs
+                uint4 ha[4], mi[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { ha[u] = T.hit[u]; mi[u] = T.miss[u]; }
+                for (uint32_t q = 0; q < nz; q += 4) {  // (rows are padded with identity columns up to the tile size; dim % 8 == 0)
+                    uint4 hn[4], mn[4];
+                    const uint32_t qn = (q + 4 < (uint32_t)kScanTile) ? q + 4 : q;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { hn[u] = T.hit[qn + u]; mn[u] = T.miss[qn + u]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        out[q + u] = s;
+                        const bool hit = ha[u].x * s + ha[u].y <= kLim5;
+                        const uint32_t sh = ha[u].z * s + ha[u].w, sn = mi[u].x * s + mi[u].y;
+                        s = hit ? sh : sn;
                     }
-                    if (blk) {  // `continue`: no decoration draws and no trailing draw
-                        s = sb;
-                        continue;
-                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { ha[u] = hn[u]; mi[u] = mn[u]; }
                 }
-                // draws after the body: r1 (% 5), [grass type], r2 (% 71), r3 (% 420), [tree], trailing — every candidate is an
-                // affine function of sb, so they are all evaluated side by side and selected by the % 5 outcome
-                const uint32_t r1 = A[1] * sb + C[1];
-                const bool hit5 = divisible(r1, inv5, lim5);
-                const uint32_t g = A[2] * sb + C[2];                 // grass type draw when hit5, else r2
-                const uint32_t r2 = hit5 ? A[3] * sb + C[3] : g;
-                const uint32_t r3a = A[3] * sb + C[3], r3b = A[4] * sb + C[4];
-                const uint32_t r3 = hit5 ? r3b : r3a;
-                const bool t420 = hit5 ? ((r3b & 3u) == 0u && divisible(r3b >> 2, inv105, lim105)) : ((r3a & 3u) == 0u && divisible(r3a >> 2, inv105, lim105));
-                uint32_t word = 0;
-                if (hit5) word = 7u + g % 5u;                            // grass blade model, not solid (procgen.zig:42)
-                if (divisible(r2, inv71, lim71)) word = 12u | kSolid;    // flower (procgen.zig:45)
-                if (word) deco[i] = word;
-                s = (hit5 ? A[5] * sb + C[5] : A[4] * sb + C[4]);        // ... and the trailing draw
-                if (t420 && x < 500u && z < 500u && x > 5u && z > 5u && x + 2u < dim && z + 2u < dim) {  // place_tree (procgen.zig:47-48, 55-70)
-                    const uint32_t th = (r3 * kLcgA + kLcgC) % 4u + 4u;
-                    if (n_trees < max_trees) trees[n_trees] = Tree{x, z, h, r3};
-                    else *status = 2u;
-                    ++n_trees;
-                    last_tree_x = (int)x;
-                    for (uint32_t a = 0; a < 3; ++a)
-                        for (uint32_t c = 0; c < 3; ++c) {
-                            if (a == 0 && c == 0) continue;  // this column is done
-                            const uint32_t r = (x + a) % 3u;
-                            const size_t col = (size_t)r * dim + (z + c);
-                            const uint32_t nb = n_blocked[col];
-                            if (nb >= (uint32_t)kMaxRanges) { *status = 1u; continue; }
-                            const uint32_t lo = (a == 1 && c == 1) ? h : h + th;  // trunk column: trunk + canopy are one run
-                            blocked[col * kMaxRanges + nb] = make_ushort2((unsigned short)lo, (unsigned short)(h + th + 2u));
-                            n_blocked[col] = (uint8_t)(nb + 1u);
-                            row_dirty[r] = true;
+            } else {
+                const uint32_t r = x % 3u;
+                uint32_t lo = blk_lo[r], hi = blk_hi[r];  // columns of this row that carry tree ranges (refreshed when a tree is planted)
+                const bool plantable = x > 5u && x < 500u && x + 2u < dim;
+                uint4 ha = T.hit[0], mi = T.miss[0];
+                uint32_t h = T.h[0];
+                for (uint32_t q = 0; q < nz; ++q) {
+                    const uint32_t z = z0 + q;
+                    const uint4 ha_n = T.hit[q + 1 < (uint32_t)kScanTile ? q + 1 : q], mi_n = T.miss[q + 1 < (uint32_t)kScanTile ? q + 1 : q];
+                    const uint32_t h_n = T.h[q + 1 < (uint32_t)kScanTile ? q + 1 : q];
+                    out[q] = s;
+                    const bool hit = ha.x * s + ha.y <= kLim5;
+                    const uint32_t sh = ha.z * s + ha.w, sn = mi.x * s + mi.y, s3 = mi.z * s + mi.w;
+                    const uint32_t r3 = hit ? sn : s3;  // the % 420 draw: L^4 of the body end after a hit, L^3 after a miss
+                    const uint32_t s_in = s;
+                    s = hit ? sh : sn;
+                    const bool tree = (r3 & 3u) == 0u && divisible(r3, kInv105, kLim105);
+                    if (h > 16u && (tree || (z >= lo && z <= hi))) {  // rare: a tree to plant, or tree blocks over this column
+                        bool blk = false;
+                        if (z >= lo && z <= hi) {  // procgen.zig:37-38: a tree block already at (x, vh, z)?
+                            for (uint32_t w = 0; w < n_blocked[r * dim + z]; ++w) {
+                                const ushort2 rg = blocked[((size_t)r * dim + z) * kMaxRanges + w];
+                                blk = blk || (h >= rg.x && h <= rg.y);
+                            }
                         }
-                    const uint2 jt = __ldg(&jump[28u + th]);  // trunk height + th trunk types + 27 leaves
-                    s = (jt.x * r3 + jt.y) * kLcgA + kLcgC;   // ... and the trailing draw
+                        if (blk) {  // `continue`: the body draws only — no decoration draws, no trailing draw
+                            const uint2 j = __ldg(&jump[body_draws(h)]);
+                            skipped[(size_t)x * dim + z] = 1;
+                            s = j.x * s_in + j.y;
+                        } else if (tree && plantable && z > 5u && z < 500u && z + 2u < dim) {
+                            // place_tree (procgen.zig:47-48, 55-70)
+                            const uint32_t th = (r3 * kLcgA + kLcgC) % 4u + 4u;
+                            if (n_trees < max_trees) trees[n_trees] = Tree{x, z, h, r3};
+                            else *status = 2u;
+                            ++n_trees;
+                            for (uint32_t a = 0; a < 3; ++a)
+                                for (uint32_t c = 0; c < 3; ++c) {
+                                    if (a == 0 && c == 0) continue;  // this column is done
+                                    const uint32_t ra = (x + a) % 3u;
+                                    const size_t col = (size_t)ra * dim + (z + c);
+                                    const uint32_t nb = n_blocked[col];
+                                    if (nb >= (uint32_t)kMaxRanges) { *status = 1u; continue; }
+                                    const uint32_t rlo = (a == 1 && c == 1) ? h : h + th;  // trunk column: trunk + canopy are one run
+                                    blocked[col * kMaxRanges + nb] = make_ushort2((unsigned short)rlo, (unsigned short)(h + th + 2u));
+                                    n_blocked[col] = (uint8_t)(nb + 1u);
+                                    row_dirty[ra] = true;
+                                    blk_lo[ra] = min(blk_lo[ra], z + c);
+                                    blk_hi[ra] = max(blk_hi[ra], z + c);
+                                }
+                            lo = blk_lo[r]; hi = blk_hi[r];
+                            const uint2 jt = __ldg(&jump[28u + th]);  // trunk height + th trunk types + 27 leaves
+                            s = (jt.x * r3 + jt.y) * kLcgA + kLcgC;   // ... and the trailing draw
+                        }
+                    }
+                    ha = ha_n; mi = mi_n; h = h_n;
                 }
             }
         }
+        __syncthreads();
     }
-    *n_trees_out = n_trees;
-    *final_seed = s;
+    if (threadIdx.x == 0) {
+        *n_trees_out = n_trees;
+        *final_seed = s;
+    }
+}
+
+// Decoration of every column from its start state (parallel): grass blade when r1 % 5 == 0, flower when r2 % 71 == 0
+// (procgen.zig:40-45); none for columns the scan skipped (`continue`) or at most 16 high.
+__global__ void deco_kernel(const uint16_t *__restrict__ vh, const uint32_t *__restrict__ seeds, const uint8_t *__restrict__ skipped,
+                            const uint2 *__restrict__ jump, size_t n_col, uint32_t *__restrict__ deco) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_col) return;
+    const uint32_t h = vh[i];
+    uint32_t word = 0;
+    if (h > 16u && !skipped[i]) {
+        const uint2 j = __ldg(&jump[body_draws(h)]);
+        uint32_t r = lcg(j.x * seeds[i] + j.y);  // r1
+        if (divisible(r, kInv5, kLim5)) {
+            r = lcg(r);
+            word = 7u + r % 5u;                  // grass blade model, not solid
+        }
+        r = lcg(r);                              // r2
+        if (divisible(r, kInv71, kLim71)) word = 12u | kSolid;
+    }
+    deco[i] = word;
 }
 
 __device__ __forceinline__ unsigned long long touch_key(uint32_t x, uint32_t z, uint32_t ev) {

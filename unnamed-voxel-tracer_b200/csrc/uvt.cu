@@ -11,6 +11,7 @@
 #include <nccl.h>  // types and prototypes only: the library is bound at run time (dlopen), see NcclApi
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -896,6 +897,10 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
     UVT_REQUIRE(c, c->h_chunks && c->h_bricks, "no world allocated");
     UVT_REQUIRE(c, n_bricks <= c->h_capacity, "n_bricks exceeds the pool capacity");
     const size_t n_chunks = (size_t)c->cd * c->cd * c->cd;
+    const bool trace = std::getenv("UVT_TRACE_COMMIT") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    auto t_phase = now();
     // every chunk entry must name a committed brick
     // (checked on the host: a bad index would be an out-of-bounds device read)
     for (size_t i = 0; i < n_chunks; ++i)
@@ -913,30 +918,40 @@ int uvt_world_commit(uvt_ctx *c, size_t n_bricks) {
     UVT_CUDA(c, cudaMemcpyAsync(c->d_chunks, c->h_chunks, n_chunks * 4, cudaMemcpyHostToDevice, c->stream));
     if (n_bricks) UVT_CUDA(c, cudaMemcpyAsync(c->d_bricks, c->h_bricks, n_bricks * 2048, cudaMemcpyHostToDevice, c->stream));
 
-    // material table: the distinct block words, ascending
+    if (trace) { cudaStreamSynchronize(c->stream); std::fprintf(stderr, "[uvt commit] validate + upload %.1f ms\n", ms_since(t_phase)); t_phase = now(); }
+    // material table: the distinct block words, ascending (collected on the device from the uploaded bricks)
     c->mat_words.assign(1, 0u);
-    std::unordered_map<uint32_t, uint32_t> ids;
     const size_t n_words = n_bricks * 512;
     bool overflow = false;
-    uint32_t last_word = 0;
-    for (size_t i = 0; i < n_words && !overflow; ++i) {
-        const uint32_t wd = c->h_bricks[i];
-        if (wd == 0 || wd == last_word) continue;
-        last_word = wd;
-        if (ids.find(wd) == ids.end()) {
+    if (n_words) {
+        uint32_t *d_set = nullptr;
+        UVT_CUDA(c, cudaMalloc(&d_set, (kWordSetSlots + 1) * 4));
+        cudaError_t e = cudaMemsetAsync(d_set, 0, (kWordSetSlots + 1) * 4, c->stream);
+        distinct_words_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_bricks, n_words, d_set, d_set + kWordSetSlots);
+        c->launches++;
+        std::vector<uint32_t> set(kWordSetSlots + 1);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(set.data(), d_set, set.size() * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(d_set);
+        if (e != cudaSuccess) return set_error(c, UVT_ERR_CUDA, "collecting the block words failed: %s", cudaGetErrorString(e));
+        overflow = set[kWordSetSlots] != 0;
+        for (uint32_t k = 0; k < kWordSetSlots && !overflow; ++k) {
+            if (set[k] == 0) continue;
             if (c->mat_words.size() >= kMatLimit) { overflow = true; break; }  // ids >= kMatLimit encode clearances
-            ids.emplace(wd, (uint32_t)c->mat_words.size());
-            c->mat_words.push_back(wd);
+            c->mat_words.push_back(set[k]);
         }
+        if (overflow) c->mat_words.resize(1);
     }
     std::sort(c->mat_words.begin() + 1, c->mat_words.end());  // canonical ids: the same materials always get the same ids
     c->compact_ok = !overflow;
     c->incremental_ok = false;
+    if (trace) { std::fprintf(stderr, "[uvt commit] material scan %.1f ms\n", ms_since(t_phase)); t_phase = now(); }
     if (c->compact_ok) {
         int rc = build_compact(c, n_bricks, n_words);
         if (rc != UVT_OK) return rc;
     }
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (trace) std::fprintf(stderr, "[uvt commit] build_compact %.1f ms\n", ms_since(t_phase));
     c->n_bricks = n_bricks;
     c->world_committed = true;
     c->materials_dirty = true;
@@ -1882,13 +1897,13 @@ int uvt_world_procgen_plan(uvt_ctx *c, float offset_x, float offset_y, size_t *n
     uint2 *d_jump = nullptr;
     float *d_grad = nullptr;
     ushort2 *d_blocked = nullptr;
-    uint8_t *d_nblocked = nullptr;
+    uint8_t *d_nblocked = nullptr, *d_skipped = nullptr;
     uint32_t *d_misc = nullptr;  // [0] n_trees [1] status [2] final seed [3] n_touched
     unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
     uint32_t *d_idx = nullptr, *d_idx2 = nullptr;
     void *d_tmp = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_jump); cudaFree(d_grad); cudaFree(d_blocked); cudaFree(d_nblocked); cudaFree(d_misc);
+        cudaFree(d_jump); cudaFree(d_grad); cudaFree(d_blocked); cudaFree(d_nblocked); cudaFree(d_skipped); cudaFree(d_misc);
         cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_tmp);
     };
 #define UVT_PG(expr)                                                                                                    \
@@ -1908,6 +1923,7 @@ int uvt_world_procgen_plan(uvt_ctx *c, float offset_x, float offset_y, size_t *n
     UVT_PG(cudaMalloc(&d_grad, sizeof grad));
     UVT_PG(cudaMalloc(&d_blocked, (size_t)3 * dim * pg::kMaxRanges * sizeof(ushort2)));
     UVT_PG(cudaMalloc(&d_nblocked, (size_t)3 * dim));
+    UVT_PG(cudaMalloc(&d_skipped, n_col));
     UVT_PG(cudaMalloc(&d_misc, 16));
     UVT_PG(cudaMalloc(&d_keys, n_chunks * 8));
     UVT_PG(cudaMalloc(&d_keys2, n_chunks * 8));
@@ -1915,16 +1931,17 @@ int uvt_world_procgen_plan(uvt_ctx *c, float offset_x, float offset_y, size_t *n
     UVT_PG(cudaMalloc(&d_idx2, n_chunks * 4));
     UVT_PG(cudaMemcpyAsync(d_jump, jump.data(), jump.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
     UVT_PG(cudaMemcpyAsync(d_grad, grad, sizeof grad, cudaMemcpyHostToDevice, c->stream));
-    UVT_PG(cudaMemsetAsync(c->pgen.deco, 0, n_col * 4, c->stream));
+    UVT_PG(cudaMemsetAsync(d_skipped, 0, n_col, c->stream));
     UVT_PG(cudaMemsetAsync(d_nblocked, 0, (size_t)3 * dim, c->stream));
     UVT_PG(cudaMemsetAsync(d_misc, 0, 16, c->stream));
     UVT_PG(cudaMemsetAsync(d_keys, 0xFF, n_chunks * 8, c->stream));
     UVT_PG(cudaMemsetAsync(c->d_chunks, 0, n_chunks * 4, c->stream));
 
     pg::heights_kernel<<<dim3((dim + 127) / 128, dim), 128, 0, c->stream>>>(d_grad, dim, offset_x, offset_y, c->pgen.vh);
-    pg::scan_kernel<<<1, 32, 0, c->stream>>>(c->pgen.vh, dim, d_jump, 0x46AE4Fu, c->pgen.seeds, c->pgen.deco, c->pgen.trees, max_trees, d_misc,
-                                             d_blocked, d_nblocked, d_misc + 1, d_misc + 2);
-    c->launches += 2;
+    pg::scan_kernel<<<1, pg::kScanThreads, 0, c->stream>>>(c->pgen.vh, dim, d_jump, 0x46AE4Fu, c->pgen.seeds, d_skipped, c->pgen.trees, max_trees, d_misc,
+                                                           d_blocked, d_nblocked, d_misc + 1, d_misc + 2);
+    pg::deco_kernel<<<(unsigned)((n_col + 255) / 256), 256, 0, c->stream>>>(c->pgen.vh, c->pgen.seeds, d_skipped, d_jump, n_col, c->pgen.deco);
+    c->launches += 3;
     uint32_t misc[4] = {0, 0, 0, 0};
     UVT_PG(cudaMemcpyAsync(misc, d_misc, 16, cudaMemcpyDeviceToHost, c->stream));
     UVT_PG(cudaStreamSynchronize(c->stream));
