@@ -26,9 +26,18 @@ class _World(ctypes.Structure):
     _fields_ = [("dim", ctypes.c_uint32), ("chunks", ctypes.c_void_p), ("bricks", ctypes.c_void_p), ("atlas", ctypes.c_void_p)]
 
 
+MAX_ENTITIES = 32
+ENTITY_POSITIONS = ((256., 21., 256.), (251., 21., 259.), (253., 21., 256.), (251., 21., 256.), (257., 21., 261.))  # map.glsl:173-179
+
+
+class _Entities(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_uint32), ("n", ctypes.c_uint32), ("pos", (ctypes.c_float * 3) * MAX_ENTITIES),
+                ("model", ctypes.c_void_p), ("size", ctypes.c_uint32), ("max_steps", ctypes.c_uint32)]
+
+
 class _Params(ctypes.Structure):
     _fields_ = [("map_dim", ctypes.c_uint32), ("primary_max_steps", ctypes.c_uint32), ("shadow_max_steps", ctypes.c_uint32),
-                ("epsilon", ctypes.c_float), ("entities", ctypes.c_uint32)]
+                ("epsilon", ctypes.c_float), ("entities", ctypes.c_uint32), ("ent", ctypes.POINTER(_Entities))]
 
 
 class _Hit(ctypes.Structure):
@@ -69,6 +78,8 @@ def lib():
         L.orc_trace_map.argtypes = [ctypes.POINTER(_World), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(_Hit)]
         L.orc_trace_entities.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float]
         L.orc_trace_entities.restype = ctypes.c_int
+        L.orc_trace_entities_ex.argtypes = [ctypes.POINTER(_World), ctypes.POINTER(_Entities), ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_float, ctypes.POINTER(_Hit)]
         L.orc_primary_ray.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                       ctypes.c_uint32, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_primary.argtypes = [ctypes.POINTER(_World), ctypes.c_void_p, ctypes.POINTER(_Params), ctypes.c_uint32, ctypes.c_uint32,
@@ -120,8 +131,44 @@ class World:
         self._c = _World(self.dim, self.chunks.ctypes.data, self.bricks.ctypes.data, self.atlas.ctypes.data)
 
 
-def params(map_dim, primary_max_steps=192, shadow_max_steps=48, epsilon=0.001, entities=True):
-    return _Params(int(map_dim), int(primary_max_steps), int(shadow_max_steps), float(np.float32(epsilon)), 1 if entities else 0)
+def entities(mode="models", positions=None, model=None, size=8, max_steps=64):
+    """The entity set of traceEntities (map.glsl:172-248).  mode "boxes" = the reference as it runs (early return at :199),
+    "models" = the code behind that return made live + the primary composite (primary.comp.glsl:45-54).  Defaults are the
+    literals of the text; model=None reads texels [0,8)^3 of the atlas like `imageLoad(model, ivec3(pos) & 7)`."""
+    e = _Entities()
+    e.mode = {"boxes": 0, "models": 1}[mode]
+    pos = np.asarray(ENTITY_POSITIONS if positions is None else positions, dtype=np.float32).reshape(-1, 3)
+    assert 0 < len(pos) <= MAX_ENTITIES
+    e.n = len(pos)
+    for i, q in enumerate(pos):
+        for k in range(3):
+            e.pos[i][k] = float(q[k])
+    e.size, e.max_steps = int(size), int(max_steps)
+    if model is not None:
+        m = np.ascontiguousarray(model, dtype=np.uint32).reshape(-1)
+        assert m.size == size ** 3 and size in (8, 16, 32)
+        e._keep = m
+        e.model = m.ctypes.data
+    else:
+        assert size == 8
+    return e
+
+
+def params(map_dim, primary_max_steps=192, shadow_max_steps=48, epsilon=0.001, entities=True, ent=None):
+    p = _Params(int(map_dim), int(primary_max_steps), int(shadow_max_steps), float(np.float32(epsilon)), 1 if entities else 0,
+                ctypes.pointer(ent) if ent is not None else None)
+    p._keep = ent
+    return p
+
+
+def trace_entities_ex(world, ent, origin, direction, max_distance, epsilon=0.001):
+    o = np.asarray(origin, dtype=np.float32)
+    d = np.asarray(direction, dtype=np.float32)
+    h = _Hit()
+    lib().orc_trace_entities_ex(ctypes.byref(world._c), ctypes.byref(ent), float(np.float32(epsilon)), o.ctypes.data, d.ctypes.data,
+                                float(np.float32(max_distance)), ctypes.byref(h))
+    return {"data": h.data, "hit_pos": tuple(h.hit_pos), "normal": tuple(h.normal), "p": tuple(h.p), "face": h.face,
+            "entity": h.block, "trips": h.trips, "exit_kind": h.exit_kind}
 
 
 def trace_map(world, origin, direction, max_steps):

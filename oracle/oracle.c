@@ -229,6 +229,102 @@ int orc_trace_entities(const float o[3], const float d[3], float max_distance) {
     return 0;
 }
 
+/* traceEntities in full: assets/shaders/map.glsl:172-248 with the early `return HitInfo(0xFFFFFFFF, ...)` of :199 removed
+ * when e->mode == 1.  Generalised only where the text has literals: the entity list (positions[], :173-179),
+ * the model edge `bounds` (:203; the box edge follows as size/8 blocks so a voxel keeps the world's sub-voxel size) and
+ * the step cap (:214).  With the defaults (5 literal positions, size 8, cap 64, model = atlas texels [0,8)^3) this is the
+ * text as written.  Note what the text does NOT do: no zero patch of rayDir (sign(0) = 0 makes that axis "negative"
+ * with an infinite reciprocal), no EPSILON on `withinGridCoords`. */
+void orc_trace_entities_ex(const orc_world *w, const orc_entities *e, float epsilon, const float o[3], const float d[3],
+                           float max_distance, orc_hit *out) {
+    memset(out, 0, sizeof *out);
+    out->p[0] = out->p[1] = out->p[2] = 0xFFFFFFFFu;
+    out->distance = -1.0f;
+    out->exit_kind = 1;
+    const int32_t S = (int32_t)e->size;
+    const float edge = (float)e->size / 8.0f; /* 1.0 for the literal 8^3 model: positions[i] + vec3(1.) */
+    float prev_d = INFINITY; /* :182 */
+    int id = -1;
+    for (uint32_t i = 0; i < e->n; ++i) { /* :186-196 */
+        const float dx = o[0] - e->pos[i][0], dy = o[1] - e->pos[i][1], dz = o[2] - e->pos[i][2];
+        if (sqrtf(dx * dx + dy * dy + dz * dz) >= max_distance) continue;
+        const float bmax[3] = {e->pos[i][0] + edge, e->pos[i][1] + edge, e->pos[i][2] + edge};
+        float tn, tf;
+        intersect_aabb(o, d, e->pos[i], bmax, &tn, &tf);
+        if (tf >= tn && prev_d >= tf) {
+            id = (int)i;
+            prev_d = tf;
+        }
+    }
+    if (id < 0) return;
+    const float *P = e->pos[id];
+    const float bmax[3] = {P[0] + edge, P[1] + edge, P[2] + edge};
+    float tn, tf;
+    intersect_aabb(o, d, P, bmax, &tn, &tf); /* :198 */
+    if (!(tf >= tn)) return;
+    if (e->mode == 0) { /* :199-201 as it runs */
+        out->data = 0xFFFFFFFFu;
+        for (int k = 0; k < 3; ++k) out->hit_pos[k] = P[k];
+        out->block = (uint32_t)id;
+        out->exit_kind = 3;
+        return;
+    }
+    /* :203-211 */
+    const float t0 = gmax(tn, 0.0f);
+    float ro[3], inv[3], wi[3];
+    int32_t sgn[3], pos[3], g[3];
+    for (int k = 0; k < 3; ++k) {
+        ro[k] = o[k] + t0 * d[k];
+        sgn[k] = f2i(gsign(d[k]));
+        pos[k] = (1 + sgn[k]) >> 1;
+        inv[k] = 1.0f / d[k];
+        g[k] = f2i((ro[k] - epsilon - P[k]) * 8.0f); /* :211 */
+        wi[k] = (ro[k] - P[k]) * 8.0f - (float)g[k];  /* :212 */
+    }
+    int min_idx = 0; /* :208 */
+    uint32_t trip;
+    for (trip = 0; trip < e->max_steps; ++trip) { /* :214 */
+        if (g[0] >= S || g[1] >= S || g[2] >= S || g[0] < 0 || g[1] < 0 || g[2] < 0) { /* :215, :243 */
+            out->exit_kind = 2;
+            break;
+        }
+        uint32_t p[3];
+        for (int k = 0; k < 3; ++k) p[k] = ((uint32_t)g[k] + f2u(wi[k])) & (uint32_t)(S - 1); /* :216, :218 `& 7` */
+        const uint32_t block = e->model ? e->model[(size_t)p[0] + (size_t)S * ((size_t)p[1] + (size_t)S * (size_t)p[2])]
+                                        : w->atlas[(size_t)p[0] + 256u * ((size_t)p[1] + 256u * (size_t)p[2])];
+        if (block != 0) { /* :220-230 */
+            uint32_t face = 0;
+            if (min_idx == 0) face = (uint32_t)(-pos[0] + 2);
+            if (min_idx == 1) face = (uint32_t)(-pos[1] + 4);
+            if (min_idx == 2) face = (uint32_t)(-pos[2] + 6);
+            static const float normals[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+            out->data = block;
+            for (int k = 0; k < 3; ++k) {
+                out->hit_pos[k] = P[k] + ((float)g[k] + wi[k]) / 8.0f; /* :230: world space */
+                out->normal[k] = normals[face - 1][k];
+                out->p[k] = p[k];
+            }
+            out->face = face;
+            out->block = (uint32_t)id;
+            out->exit_kind = 3;
+            out->trips = trip + 1;
+            return;
+        }
+        for (int k = 0; k < 3; ++k) { /* :232-235 */
+            g[k] += f2i(wi[k]);
+            wi[k] = wi[k] - floorf(wi[k]);
+        }
+        float t[3]; /* :238-243 */
+        for (int k = 0; k < 3; ++k) t[k] = ((float)pos[k] - wi[k]) * inv[k];
+        min_idx = t[0] < t[1] ? (t[0] < t[2] ? 0 : 2) : (t[1] < t[2] ? 1 : 2);
+        g[min_idx] += sgn[min_idx];
+        const float tm = t[min_idx];
+        for (int k = 0; k < 3; ++k) wi[k] += d[k] * tm;
+        wi[min_idx] = (float)(1 - pos[min_idx]) * 0.999f;
+    }
+    out->trips = trip;
+}
+
 /* Ray generation: assets/shaders/primary.comp.glsl:31-43.  tan_half_fov = tanf(fov / 2). */
 void orc_primary_ray(const orc_camera *cam, float tan_half_fov, uint32_t W, uint32_t H, uint32_t px, uint32_t py,
                      uint32_t map_dim, float epsilon, float origin[3], float dir[3], float start[3]) {
@@ -287,6 +383,28 @@ static void primary_pixel(const orc_world *w, const orc_camera *cam, const orc_p
     orc_hit h;
     orc_trace_map(w, s, d, (int)prm->primary_max_steps, &h);
     add_counters(cnt, &h);
+    if (prm->ent && prm->ent->mode == 1) { /* :45-54, commented out in the reference: the entity composite */
+        const float ex = o[0] - h.hit_pos[0] / 8.0f, ey = o[1] - h.hit_pos[1] / 8.0f, ez = o[2] - h.hit_pos[2] / 8.0f;
+        orc_hit eh;
+        orc_trace_entities_ex(w, prm->ent, prm->epsilon, o, d, sqrtf(ex * ex + ey * ey + ez * ez) + prm->epsilon, &eh); /* :47 */
+        if (eh.data != 0) {
+            *albedo = eh.data;                                                        /* :50 */
+            *normal = pack_rgba8(eh.normal[0], eh.normal[1], eh.normal[2], 1.0f);     /* :51 */
+            for (int k = 0; k < 3; ++k) position[k] = eh.hit_pos[k];                  /* :52: world space, no ceil/8 */
+            position[3] = 1.0f;
+            if (rec) {
+                const float dx = eh.hit_pos[0] - o[0], dy = eh.hit_pos[1] - o[1], dz = eh.hit_pos[2] - o[2];
+                rec->px = eh.p[0]; rec->py = eh.p[1]; rec->pz = eh.p[2];
+                rec->block = 0x80000000u | eh.block;
+                rec->color = eh.data;
+                rec->distance = sqrtf(dx * dx + dy * dy + dz * dz);
+                rec->trips = (uint16_t)eh.trips;
+                rec->face = (uint8_t)eh.face;
+                rec->exit_kind = 3;
+            }
+            return;
+        }
+    }
     if (h.data != 0) { /* :58-62 */
         *albedo = h.data;
         *normal = pack_rgba8(h.normal[0], h.normal[1], h.normal[2], 1.0f);
@@ -379,7 +497,14 @@ void orc_secondary(const orc_world *w, const orc_params *prm, uint32_t W, uint32
                 int ent = 0;
                 if (prm->entities) {
                     const float dx = o[0] - h.hit_pos[0] / 8.0f, dy = o[1] - h.hit_pos[1] / 8.0f, dz = o[2] - h.hit_pos[2] / 8.0f;
-                    ent = orc_trace_entities(o, SUN_DIR, sqrtf(dx * dx + dy * dy + dz * dz)); /* :42 */
+                    const float maxd = sqrtf(dx * dx + dy * dy + dz * dz);
+                    if (prm->ent) {
+                        orc_hit eh;
+                        orc_trace_entities_ex(w, prm->ent, prm->epsilon, o, SUN_DIR, maxd, &eh);
+                        ent = eh.data != 0;
+                    } else {
+                        ent = orc_trace_entities(o, SUN_DIR, maxd); /* :42 */
+                    }
                 }
                 const float a = (ent || h.data != 0) ? -0.3f : 0.3f; /* :45-48 */
                 illum[i] = pack_rgba8(SUN_DIR[0], SUN_DIR[1], SUN_DIR[2], a); /* :50 */

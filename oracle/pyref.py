@@ -5,7 +5,7 @@ numpy float32 array per GLSL vec3), independently of oracle.c, so that agreement
 two pins the C oracle's reading of the shader (there is no runnable reference here; SURVEY
 §8c).  Slow: use on small cases only.
 
-Follows assets/shaders/map.glsl:21-47,57-60,83-201, primary.comp.glsl:23-68,
+Follows assets/shaders/map.glsl:21-47,57-60,83-248, primary.comp.glsl:23-68,
 secondary.comp.glsl:18-50.
 """
 import numpy as np
@@ -152,6 +152,66 @@ def trace_entities(ro, rd, max_distance):
     pos = np.array(ENTITY_POSITIONS[chosen], dtype=F)
     near, far = intersect_aabb(ro, rd, pos, (pos + F(1.0)).astype(F))
     return bool(far >= near)
+
+
+def trace_entities_models(model, ro, rd, max_distance, positions=ENTITY_POSITIONS, size=8, max_steps=64):
+    """map.glsl:172-248 read with the early return of :199 deleted (the sub-model DDA made live).
+    `model[z, y, x]` = size^3 texels; box edge = size / 8 blocks (1 for the literal 8^3).
+    Returns dict(data, hit_pos, normal, face, p, entity, trips)."""
+    ro = np.asarray(ro, dtype=F)
+    rd = np.asarray(rd, dtype=F)
+    edge = F(F(size) / F(8.0))
+    miss = {"data": 0, "hit_pos": (0.0, 0.0, 0.0), "normal": (0.0, 0.0, 0.0), "face": 0, "p": None, "entity": None, "trips": 0}
+    prev_d = F(np.inf)
+    chosen = None
+    for i, pos in enumerate(positions):
+        pos = np.array(pos, dtype=F)
+        diff = (ro - pos).astype(F)
+        sq = (diff * diff).astype(F)
+        if np.sqrt(F(F(sq[0] + sq[1]) + sq[2]), dtype=F) >= max_distance:
+            continue
+        near, far = intersect_aabb(ro, rd, pos, (pos + edge).astype(F))
+        if far >= near and prev_d >= far:
+            chosen, prev_d = i, far
+    if chosen is None:
+        return miss
+    pos = np.array(positions[chosen], dtype=F)
+    near, far = intersect_aabb(ro, rd, pos, (pos + edge).astype(F))
+    if not far >= near:
+        return miss
+    bounds = size
+    t0 = near if F(0.0) < near else F(0.0)                       # max(hit.x, 0)
+    ro = (ro + (rd * t0).astype(F)).astype(F)                    # :204
+    sgn = np.array([1 if c > 0 else (-1 if c < 0 else 0) for c in rd], dtype=np.int64)   # ivec3(sign(rayDir))
+    positivity = (1 + sgn) >> 1
+    with np.errstate(divide="ignore"):
+        inv = (F(1.0) / rd).astype(F)
+    min_idx = 0
+    g = _ivec((((ro - EPSILON).astype(F) - pos).astype(F) * F(8.0)).astype(F))            # :211
+    w = (((ro - pos).astype(F) * F(8.0)).astype(F) - g.astype(F)).astype(F)               # :212
+    trips = 0
+    for _ in range(max_steps):
+        if (g >= bounds).any() or (g < 0).any():
+            break
+        trips += 1
+        p = ((g & 0xFFFFFFFF) + _uvec(w)) & 0xFFFFFFFF
+        q = p & (size - 1)
+        block = int(model[q[2], q[1], q[0]])
+        if block != 0:
+            face = [2 - positivity[0], 4 - positivity[1], 6 - positivity[2]][min_idx]
+            hp = (pos + ((g.astype(F) + w).astype(F) / F(8.0)).astype(F)).astype(F)       # :230
+            return {"data": block, "hit_pos": tuple(float(x) for x in hp), "normal": tuple(float(x) for x in NORMALS[face - 1]),
+                    "face": int(face), "p": tuple(int(x) for x in q), "entity": chosen, "trips": trips}
+        g = g + _ivec(w)
+        w = (w - np.floor(w)).astype(F)
+        with np.errstate(invalid="ignore"):
+            t = ((positivity.astype(F) - w).astype(F) * inv).astype(F)
+        min_idx = (0 if t[0] < t[2] else 2) if t[0] < t[1] else (1 if t[1] < t[2] else 2)
+        g[min_idx] += sgn[min_idx]
+        with np.errstate(invalid="ignore"):
+            w = (w + (rd * t[min_idx]).astype(F)).astype(F)
+        w[min_idx] = F(F(1 - positivity[min_idx]) * F(0.999))
+    return dict(miss, trips=trips)
 
 
 def primary_ray(cam_pos, cam_mat, fov, W, H, px, py, map_dim):

@@ -94,7 +94,7 @@ def main():
     L = lambda m, s=1: find_line(tr, m, s)
     fast = L("trace_map_fast(const WorldCompact &w")
     loop = L("for (;;) {", fast)
-    short_lo = L("if (DENSE && COUNT != 1 && slow) {", loop)
+    short_lo = L("DENSE && COUNT != 1 && slow) {", loop)
     gen_lo = L("if (slow) {", short_lo)
     walk = L("column-tops walk: many free trips at once", gen_lo)
     vote = L("how many trips can the whole warp run", walk)
