@@ -85,7 +85,8 @@ typedef struct uvt_hit {
     float    distance;   /* length(hit_pos/8 - rayOrigin) in blocks, fp32; -1 on miss            */
     uint16_t trips;      /* DDA loop trips executed (map.glsl:106)                               */
     uint8_t  face;       /* faceId 1..6 (map.glsl:119-125), 0 = miss                             */
-    uint8_t  exit_kind;  /* 0 hit, 1 step cap exhausted, 2 left the map                          */
+    uint8_t  exit_kind;  /* 0 hit, 1 step cap exhausted, 2 left the map, 3 entity (UVT_ENTITY_MODELS composite:
+                          * p = model voxel, block = 0x80000000 | entity index, trips = model-loop trips) */
 } uvt_hit;               /* 28 bytes */
 
 /* Exact per-pass traversal counters; they define the ALGORITHMIC bytes of SURVEY §8d:
@@ -199,6 +200,27 @@ int  uvt_dispatch_secondary(uvt_ctx *ctx);  /* secondary.comp.glsl main */
 int  uvt_shade(uvt_ctx *ctx);               /* blit.fragment.glsl main → RGBA8 frame */
 /* primary+secondary+shade in one launch; results identical to the three calls above */
 int  uvt_dispatch_frame(uvt_ctx *ctx);
+/* ---- entities: traceEntities (assets/shaders/map.glsl:172-248), SURVEY 8 row f3 ----------------------
+ * The reference as it runs leaves traceEntities at map.glsl:199 (five literal unit boxes intersected as lines, shadow
+ * pass only): UVT_ENTITY_BOXES, the default, compiled into the shadow kernel.  UVT_ENTITY_MODELS makes the code
+ * behind that return live — a DDA over the entity's voxel model (map.glsl:203-248) — together with the entity
+ * composite the reference keeps commented out in the primary pass (primary.comp.glsl:45-54); both then run as
+ * extra launches after the primary / secondary kernels.  MODELS turns the hit buffer on (the composite reads the
+ * terrain distance of primary.comp.glsl:47 from it): call it before uvt_resize, or expect the G-buffer to be
+ * re-created.  UVT_FLAG_ENTITIES off disables every entity test. */
+typedef enum uvt_entity_mode {
+    UVT_ENTITY_BOXES = 0,
+    UVT_ENTITY_MODELS = 1
+} uvt_entity_mode;
+int  uvt_set_entity_mode(uvt_ctx *ctx, uint32_t mode);
+/* `positions[]` of map.glsl:173-179: n <= 32 low box corners (xyz, blocks); n = 0 restores the five literals. */
+int  uvt_set_entities(uvt_ctx *ctx, const float *positions_xyz, uint32_t n);
+/* The entity model: size^3 RGBA8 texels (size 8, 16 or 32: chicken.vox is 32^3, src/game.zig:114), x fastest, then
+ * y, then z; the entity's box edge is size/8 blocks, so a model voxel is as large as a world sub-voxel.  rgba = NULL
+ * restores the text as written: `imageLoad(model, ivec3(pos) & 7)` = texels [0,8)^3 of the atlas (map.glsl:218).
+ * max_steps = the cap of the model loop (map.glsl:214), 0 = 64. */
+int  uvt_entity_model_upload(uvt_ctx *ctx, uint32_t size, const uint32_t *rgba, uint32_t max_steps);
+
 /* terrain_edit.comp.glsl: the centre pick ray, traceMap(...,64); returns the hit. */
 int  uvt_pick(uvt_ctx *ctx, uvt_hit *out);
 int  uvt_sync(uvt_ctx *ctx);
@@ -294,6 +316,9 @@ int  uvt_group_world_grow(uvt_group *g, size_t new_capacity, uint32_t **bricks_h
 int  uvt_group_world_commit(uvt_group *g, size_t n_bricks);
 int  uvt_group_world_commit_region(uvt_group *g, size_t n_bricks, const uint32_t lo[3], const uint32_t hi[3]);
 int  uvt_group_atlas_upload(uvt_group *g, uint32_t ox, uint32_t oy, uint32_t oz, uint32_t w, uint32_t h, uint32_t d, const uint32_t *rgba);
+int  uvt_group_set_entity_mode(uvt_group *g, uint32_t mode);
+int  uvt_group_set_entities(uvt_group *g, const float *positions_xyz, uint32_t n);
+int  uvt_group_entity_model_upload(uvt_group *g, uint32_t size, const uint32_t *rgba, uint32_t max_steps);
 int  uvt_group_set_camera(uvt_group *g, const uvt_camera *cam);
 int  uvt_group_resize(uvt_group *g, uint32_t width, uint32_t height);
 int  uvt_group_dispatch_frame(uvt_group *g);           /* primary + secondary + shade on every member, asynchronous */

@@ -203,8 +203,8 @@ def trace_entities_models(model, ro, rd, max_distance, positions=ENTITY_POSITION
             return {"data": block, "hit_pos": tuple(float(x) for x in hp), "normal": tuple(float(x) for x in NORMALS[face - 1]),
                     "face": int(face), "p": tuple(int(x) for x in q), "entity": chosen, "trips": trips}
         g = g + _ivec(w)
-        w = (w - np.floor(w)).astype(F)
         with np.errstate(invalid="ignore"):
+            w = (w - np.floor(w)).astype(F)
             t = ((positivity.astype(F) - w).astype(F) * inv).astype(F)
         min_idx = (0 if t[0] < t[2] else 2) if t[0] < t[1] else (1 if t[1] < t[2] else 2)
         g[min_idx] += sgn[min_idx]

@@ -1128,3 +1128,101 @@ def test_device_procgen_is_the_default_for_a_fresh_map_on_a_ctx(uvt, oracle, mod
             ctx.dispatch_frame()
             frames.append(ctx.readback("frame").copy())
     assert np.array_equal(frames[0], frames[1])
+
+
+# ---- entities done properly: map.glsl:203-248 live + the primary composite of primary.comp.glsl:45-54 ----
+ENTITY_CAMERAS = [((258.0, 25.0, 262.0), 0.5, 3.6), ((262.0, 30.0, 262.0), 0.6, 5 * np.pi / 4), ((249.0, 27.0, 262.0), 0.9, 2.2),
+                  ((254.5, 21.6, 250.0), 0.05, 0.0), ((256.5, 21.5, 256.5), 0.2, 1.0)]  # the last one sits INSIDE entity 0's box
+
+
+def assert_frame_parity(g, r):
+    assert_primary_parity(g, r)
+    assert np.array_equal(g["illumination"], r["illumination"])
+    assert channel_diff(g["frame"], r["frame"]).max() <= 1
+
+
+@pytest.mark.parametrize("case", ["atlas8", "chicken32", "boxes-custom"])
+def test_entity_models_frame_parity(uvt, oracle, w1, case):
+    import os
+    from conftest import GOLDEN
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    W, H = 256, 144
+    try:
+        if case == "atlas8":      # the text as written: five literal boxes, model = texels [0,8)^3 of the atlas
+            ctx.set_entity_mode("models")
+            ent = oracle.entities("models")
+        elif case == "chicken32":  # chicken.vox (game.zig:114) as a 32^3 model in 4-block boxes
+            m = np.load(os.path.join(GOLDEN, "chicken_32.npy"))
+            pos = [(252.0, 21.0, 254.0), (258.5, 22.25, 259.0), (246.0, 20.0, 262.0)]
+            ctx.set_entity_mode("models")
+            ctx.set_entities(pos)
+            ctx.entity_model_upload(m, 32, 256)
+            ent = oracle.entities("models", positions=pos, model=m, size=32, max_steps=256)
+        else:                      # live behaviour (boxes as lines, shadow pass only) with a custom entity list
+            pos = [(255.0, 22.0, 258.0), (259.0, 21.0, 255.0), (250.0, 23.0, 250.0), (262.0, 21.0, 262.0)]
+            ctx.set_entities(pos)
+            ent = oracle.entities("boxes", positions=pos)
+        ctx.resize(W, H)
+        prm = oracle.params(512, ent=ent)
+        seen = 0
+        for p, pitch, yaw in ENTITY_CAMERAS:
+            cam = oracle.make_camera(p, pitch_yaw_matrix(uvt, pitch, yaw))
+            r = oracle.render(sc.oracle_world, cam, W, H, prm)
+            off = oracle.render(sc.oracle_world, cam, W, H, oracle.params(512, entities=False))
+            seen += int((r["hits"]["exit_kind"] == 3).sum()) + int((r["illumination"] != off["illumination"]).sum())
+            for three in (True, False):
+                assert_frame_parity(gpu_render(ctx, cam, three_pass=three), r)
+        assert seen > 2000, seen
+    finally:
+        ctx.set_entity_mode("boxes")
+        ctx.set_entities(None)
+        ctx.entity_model_upload(None)
+    # back to the reference as it runs
+    cam = oracle.make_camera(ENTITY_CAMERAS[1][0], pitch_yaw_matrix(uvt, *ENTITY_CAMERAS[1][1:]))
+    assert_frame_parity(gpu_render(ctx, cam), oracle.render(sc.oracle_world, cam, W, H))
+
+
+def test_entity_models_with_every_dispatch_path(uvt, oracle, scene_factory):
+    """The composite and the entity shadow pass follow the frame through the pooled scheduler, the reference layout, a
+    batched dispatch and a band partition; a ctx created WITHOUT the hit buffer gets one when the mode is switched."""
+    p, pitch, yaw = ENTITY_CAMERAS[0]
+    cam = oracle.make_camera(p, pitch_yaw_matrix(uvt, pitch, yaw))
+    cam2 = oracle.make_camera(ENTITY_CAMERAS[2][0], pitch_yaw_matrix(uvt, *ENTITY_CAMERAS[2][1:]))
+    W, H = 200, 120
+    with uvt.Context(0, hit_buffer=False) as ctx:
+        sc = scene_factory(512, "procgen", ctx=ctx)
+        ctx.resize(W, H)
+        ctx.set_entity_mode("models")   # after the resize: the G-buffer is re-created with a hit buffer
+        prm = oracle.params(512, ent=oracle.entities("models"))
+        r, r2 = (oracle.render(sc.oracle_world, c, W, H, prm) for c in (cam, cam2))
+        assert (r["hits"]["exit_kind"] == 3).sum() > 300
+        for layout, sched in (("compact", "tile"), ("compact", "pool"), ("reference", "tile")):
+            ctx.set_layout(layout)
+            ctx.set_scheduler(sched)
+            assert_frame_parity(gpu_render(ctx, cam), r)
+        ctx.set_layout("compact")
+        ctx.set_scheduler("tile")
+        # batched poses
+        ctx.set_camera(np.array([cam, cam2]))
+        ctx.dispatch_frame()
+        for k, ref in enumerate((r, r2)):
+            assert np.array_equal(ctx.readback("illumination")[k], ref["illumination"])
+            assert np.array_equal(ctx.readback("hit")[k]["exit_kind"], ref["hits"]["exit_kind"])
+            assert channel_diff(ctx.readback("frame")[k], ref["frame"]).max() <= 1
+        # band partition: the union of two parts is the frame
+        ctx.set_camera(cam)
+        parts = []
+        for part in range(2):
+            ctx.set_partition(16, 2, part)
+            ctx.resize(W, H)
+            ctx.set_camera(cam)
+            ctx.dispatch_frame()
+            parts.append((ctx.readback("frame"), ctx.readback("hit")))
+        full = np.zeros((H, W), np.uint32)
+        kinds = np.zeros((H, W), np.uint8)
+        for part, (f, h) in enumerate(parts):
+            rows = [y for y in range(H) if (y // 16) % 2 == part]
+            full[rows] = f.reshape(-1, W)[:len(rows)]
+            kinds[rows] = h.reshape(-1, W)[:len(rows)]["exit_kind"]
+        assert channel_diff(full, r["frame"]).max() <= 1 and np.array_equal(kinds, r["hits"]["exit_kind"])

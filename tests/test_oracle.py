@@ -253,3 +253,99 @@ def test_pixel_list_api_equals_the_full_frame(oracle, world512, uvt):
     assert np.array_equal(p["position"].view(np.uint32), full["position"][ys, xs].view(np.uint32))
     s = oracle.secondary(world512.oracle_world, p["normal"][None, :], p["position"][None, :, :])
     assert np.array_equal(s["illumination"][0], full["illumination"][ys, xs])
+
+
+# ---- entities done properly: traceEntities with map.glsl:203-248 live ---------------------------
+def _entity_rays(rng, n, positions, edge):
+    """Rays aimed at (or near) the entity boxes from around them; every 7th has a zero direction component (the text
+    does not patch zeros here: sign(0) = 0, infinite reciprocal)."""
+    P = np.asarray(positions, np.float32)
+    lo, hi = P.min(0) - 6, P.max(0) + edge + 6
+    for i in range(n):
+        o = rng.uniform(lo, hi).astype(np.float32)
+        tgt = P[rng.integers(len(P))] + rng.uniform(-0.2, edge + 0.2, 3).astype(np.float32)
+        d = tgt - o
+        d = (d / np.linalg.norm(d)).astype(np.float32)
+        if i % 7 == 0:
+            d[rng.integers(3)] = 0.0
+        yield o, d
+
+
+def test_kat_entity_model_axis_ray(oracle, scene_factory, atlas):
+    """Hand trace of map.glsl:203-230 for a full 8^3 model: the ray (1,0,0) from (250, 21.5, 256.5) meets entity 3 at
+    (251,21,256) with tNear = 1: gridsCoords = ivec3((-0.001, 0.499, 0.499) * 8) = (0, 3, 3), withinGridCoords = (0, 1, 1),
+    the first lookup is voxel (0, 4, 4), minIdx is still 0 so faceId = 2 - rayPositivity.x = 1, hit_pos = pos + (0, 4, 4) / 8."""
+    sc = scene_factory(512, None, key="empty")
+    full = np.full(512, 0xFF112233, np.uint32)
+    ent = oracle.entities("models", model=full, size=8)
+    h = oracle.trace_entities_ex(sc.oracle_world, ent, (250.0, 21.5, 256.5), (1.0, 0.0, 0.0), 100.0)
+    assert h["data"] == 0xFF112233 and h["entity"] == 3 and h["trips"] == 1 and h["p"] == (0, 4, 4)
+    assert h["face"] == 1 and h["normal"] == (-1.0, 0.0, 0.0) and h["hit_pos"] == (251.0, 21.5, 256.5)
+    # boxes mode (the reference as it runs): data = 0xFFFFFFFF, hit_pos = positions[id]  (map.glsl:199)
+    b = oracle.trace_entities_ex(sc.oracle_world, oracle.entities("boxes"), (250.0, 21.5, 256.5), (1.0, 0.0, 0.0), 100.0)
+    assert b["data"] == 0xFFFFFFFF and b["hit_pos"] == (251.0, 21.0, 256.0)
+    # maxDistance culls on distance(rayOrigin, positions[i]) (the box CORNER), strictly: 1.118... away
+    assert oracle.trace_entities_ex(sc.oracle_world, ent, (250.0, 21.5, 256.5), (1.0, 0.0, 0.0), 1.0)["data"] == 0
+    # an empty model and the quirk of the text: rayDir is NOT zero-patched here, so t.y = (0 - 1) * (1 / 0) = -inf wins the
+    # argmin, raySign.y = 0 moves nothing, `within` turns NaN and the ray idles inside the grid until the 64-trip cap
+    e0 = oracle.entities("models", model=np.zeros(512, np.uint32), size=8)
+    h0 = oracle.trace_entities_ex(sc.oracle_world, e0, (250.0, 21.5, 256.5), (1.0, 0.0, 0.0), 100.0)
+    assert h0["data"] == 0 and h0["trips"] == 64
+    # without zero components it crosses the 8 voxels of the box and leaves: 8 x-steps plus the y/z steps on the way
+    h1 = oracle.trace_entities_ex(sc.oracle_world, e0, (250.0, 21.5, 256.5), (1.0, 0.01, 0.02), 100.0)
+    assert h1["data"] == 0 and h1["exit_kind"] == 2 and 8 <= h1["trips"] <= 10
+
+
+@pytest.mark.parametrize("case", ["atlas8", "chicken32", "custom16"])
+def test_entity_models_c_vs_python_restatement(oracle, scene_factory, models, case):
+    from oracle import pyref
+    sc = scene_factory(512, None, key="empty")
+    rng = np.random.default_rng({"atlas8": 1, "chicken32": 2, "custom16": 3}[case])
+    if case == "atlas8":      # the text as written: texels [0,8)^3 of the atlas = the first block model
+        ent, model, size, steps, pos = oracle.entities("models"), models[0].reshape(8, 8, 8), 8, 64, oracle.ENTITY_POSITIONS
+    elif case == "chicken32":
+        m = np.load(os.path.join(GOLDEN, "chicken_32.npy"))
+        pos = [(100.0, 30.0, 100.0), (110.5, 31.25, 97.0)]
+        ent, model, size, steps = oracle.entities("models", positions=pos, model=m, size=32, max_steps=256), m.reshape(32, 32, 32), 32, 256
+    else:
+        m = (rng.random(16 ** 3) < 0.04).astype(np.uint32) * rng.integers(1, 2 ** 32, 16 ** 3, dtype=np.uint32)
+        pos = [(20.0, 5.0, 20.0), (21.0, 5.5, 22.5), (23.0, 4.0, 20.0)]
+        ent, model, size, steps = oracle.entities("models", positions=pos, model=m, size=16, max_steps=40), m.reshape(16, 16, 16), 16, 40
+    hits = 0
+    for o, d in _entity_rays(rng, 1500, pos, size / 8):
+        a = oracle.trace_entities_ex(sc.oracle_world, ent, o, d, 60.0)
+        b = pyref.trace_entities_models(model, o, d, np.float32(60.0), positions=pos, size=size, max_steps=steps)
+        assert a["data"] == b["data"] and a["trips"] == b["trips"], (o, d, a, b)
+        if a["data"]:
+            hits += 1
+            assert (a["face"], a["p"], a["entity"]) == (b["face"], b["p"], b["entity"])
+            assert np.array_equal(np.array(a["hit_pos"], np.float32), np.array(b["hit_pos"], np.float32))
+    assert hits > 300, hits
+
+
+def test_entity_composite_frame_properties(uvt, oracle, world512):
+    """primary.comp.glsl:45-54 made live: entity pixels carry the model's colour, a world-space position inside the
+    entity's box and exit_kind 3; every other pixel is the frame without entities; the shadow pass then treats entity
+    surfaces like terrain.  The boxes mode reproduces the default params bit for bit."""
+    cam = oracle.make_camera((258.0, 25.0, 262.0), np.asarray(_pitch_yaw(uvt, 0.5, 3.6)))
+    W, H = 160, 90
+    base = oracle.render(world512.oracle_world, cam, W, H)
+    boxes = oracle.render(world512.oracle_world, cam, W, H, oracle.params(512, ent=oracle.entities("boxes")))
+    for k in ("albedo", "normal", "illumination", "frame"):
+        assert np.array_equal(base[k], boxes[k]), k
+    r = oracle.render(world512.oracle_world, cam, W, H, oracle.params(512, ent=oracle.entities("models")))
+    ent_px = r["hits"]["exit_kind"] == 3
+    assert 200 < ent_px.sum() < W * H // 2, ent_px.sum()
+    for k in ("albedo", "normal"):
+        assert np.array_equal(r[k][~ent_px], base[k][~ent_px])
+    p = r["position"][ent_px][:, :3]
+    ids = r["hits"]["block"][ent_px] & 0xFF
+    corner = np.asarray(oracle.ENTITY_POSITIONS, np.float32)[ids]
+    assert ((p >= corner - 1e-3) & (p <= corner + 1 + 1e-3)).all()
+    assert (r["hits"]["color"][ent_px] != 0).all() and set(np.unique(r["hits"]["face"][ent_px])) <= {1, 2, 3, 4, 5, 6}
+    assert (r["illumination"][ent_px] != 0).all()  # entity surfaces shoot shadow rays
+
+
+def _pitch_yaw(uvt, pitch, yaw):
+    from conftest import pitch_yaw_matrix
+    return pitch_yaw_matrix(uvt, pitch, yaw)

@@ -5,6 +5,8 @@
                      src/game.zig:101-113, converted by OUR .vox reader + atlas builder
                      (texel index x + 8*y + 64*z after the y/z swap of voxel.zig:106-108).
   atlas_counts.json  filled sub-voxels per model (cross-checked against SURVEY App. B.3).
+  chicken_32.npy     [32768] u32 — assets/chicken.vox (the entity model of src/game.zig:114) as 32^3 texels, x + 32*(y + 32*z),
+                     converted by voxel.load_model (same y/z swap and palette rule as the block models).
   oracle_*.npz       oracle outputs for small fixed scenes (hit buffers, G-buffers, frame, counters).
 """
 import importlib
@@ -38,6 +40,9 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     models, counts = make_atlas()
     print(len(models), "models; filled:", counts)
+    chicken = uvt.voxel.load_model(os.path.join(ASSETS, "chicken.vox"), 32)
+    np.save(os.path.join(GOLD, "chicken_32.npy"), chicken)
+    print("chicken.vox:", int((chicken != 0).sum()), "voxels of 32^3")
 
 
 def make_oracle_goldens():

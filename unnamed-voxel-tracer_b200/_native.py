@@ -20,6 +20,7 @@ P = ctypes.POINTER
 UVT_OK = 0
 UVT_ERR_INVALID, UVT_ERR_CUDA, UVT_ERR_NO_DEVICE, UVT_ERR_OOM, UVT_ERR_FORMAT, UVT_ERR_IO = -1, -2, -3, -4, -5, -6
 UVT_FLAG_HIT_BUFFER, UVT_FLAG_ENTITIES, UVT_FLAG_NO_DENSE, UVT_FLAG_FUSED_FRAME = 1, 2, 4, 8
+UVT_ENTITY_BOXES, UVT_ENTITY_MODELS = 0, 1
 UVT_LAYOUT_COMPACT, UVT_LAYOUT_REFERENCE = 0, 1
 UVT_SCHED_TILE, UVT_SCHED_POOL = 0, 1
 UVT_PIPELINE_PRIMARY, UVT_PIPELINE_SECONDARY, UVT_PIPELINE_EDIT, UVT_PIPELINE_BLIT = 0, 1, 2, 3
@@ -81,6 +82,9 @@ SIGNATURES = {
     "uvt_dispatch_secondary": (c_int, [c_p]),
     "uvt_shade": (c_int, [c_p]),
     "uvt_dispatch_frame": (c_int, [c_p]),
+    "uvt_set_entity_mode": (c_int, [c_p, c_u32]),
+    "uvt_set_entities": (c_int, [c_p, c_p, c_u32]),
+    "uvt_entity_model_upload": (c_int, [c_p, c_u32, c_p, c_u32]),
     "uvt_pick": (c_int, [c_p, c_p]),
     "uvt_sync": (c_int, [c_p]),
     "uvt_readback": (c_int, [c_p, c_int, c_p, c_size]),
@@ -119,6 +123,9 @@ SIGNATURES = {
     "uvt_group_world_commit": (c_int, [c_p, c_size]),
     "uvt_group_world_commit_region": (c_int, [c_p, c_size, P(c_u32 * 3), P(c_u32 * 3)]),
     "uvt_group_atlas_upload": (c_int, [c_p, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, c_p]),
+    "uvt_group_set_entity_mode": (c_int, [c_p, c_u32]),
+    "uvt_group_set_entities": (c_int, [c_p, c_p, c_u32]),
+    "uvt_group_entity_model_upload": (c_int, [c_p, c_u32, c_p, c_u32]),
     "uvt_group_set_camera": (c_int, [c_p, c_p]),
     "uvt_group_resize": (c_int, [c_p, c_u32, c_u32]),
     "uvt_group_dispatch_frame": (c_int, [c_p]),

@@ -165,6 +165,24 @@ int uvt_group_atlas_upload(uvt_group *g, uint32_t ox, uint32_t oy, uint32_t oz, 
     return UVT_OK;
 }
 
+int uvt_group_set_entity_mode(uvt_group *g, uint32_t mode) {
+    if (!g) return UVT_ERR_INVALID;
+    UVT_EACH(g, uvt_set_entity_mode(m, mode));
+    return UVT_OK;
+}
+
+int uvt_group_set_entities(uvt_group *g, const float *positions_xyz, uint32_t n) {
+    if (!g) return UVT_ERR_INVALID;
+    UVT_EACH(g, uvt_set_entities(m, positions_xyz, n));
+    return UVT_OK;
+}
+
+int uvt_group_entity_model_upload(uvt_group *g, uint32_t size, const uint32_t *rgba, uint32_t max_steps) {
+    if (!g) return UVT_ERR_INVALID;
+    UVT_EACH(g, uvt_entity_model_upload(m, size, rgba, max_steps));
+    return UVT_OK;
+}
+
 // ---- per frame ------------------------------------------------------------------------------------
 int uvt_group_set_camera(uvt_group *g, const uvt_camera *cam) {
     if (!g) return UVT_ERR_INVALID;

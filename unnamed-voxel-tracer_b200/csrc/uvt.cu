@@ -27,6 +27,7 @@
 #include "kernels.cuh"
 #include "pool.cuh"
 #include "procgen.cuh"
+#include "entity.cuh"
 
 using namespace uvt;
 
@@ -135,6 +136,12 @@ struct uvt_ctx {
         size_t n_bricks = 0;
         bool planned = false;
     } pgen;
+
+    // ---- entities (uvt_set_entity_mode / uvt_set_entities / uvt_entity_model_upload)
+    uint32_t ent_mode = UVT_ENTITY_BOXES;
+    std::vector<float> ent_pos;          // xyz per entity; empty: the five literal positions of map.glsl:173-179
+    uint32_t ent_size = 8, ent_steps = 64;
+    uint32_t *d_ent_model = nullptr;     // [ent_size^3]; nullptr: texels [0,8)^3 of the atlas (map.glsl:218)
 
     // ---- NCCL band exchange (uvt_nccl_init / uvt_dispatch_frame_nccl)
     ncclComm_t nccl = nullptr;
@@ -319,6 +326,25 @@ WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     return a;
 }
 
+bool ent_custom(const uvt_ctx *c) { return c->ent_mode == UVT_ENTITY_MODELS || !c->ent_pos.empty(); }
+
+EntityDev make_entities(const uvt_ctx *c) {
+    static const float literal[5][3] = {{256.f, 21.f, 256.f}, {251.f, 21.f, 259.f}, {253.f, 21.f, 256.f}, {251.f, 21.f, 256.f}, {257.f, 21.f, 261.f}};
+    EntityDev e;
+    e.mode = c->ent_mode;
+    e.size = c->d_ent_model ? c->ent_size : 8u;
+    e.max_steps = c->ent_steps;
+    e.model = c->d_ent_model ? c->d_ent_model : c->d_models;  // atlas slot 0 = texels [0,8)^3, same x + 8 * (y + 8 * z) order
+    if (c->ent_pos.empty()) {
+        e.n = 5;
+        std::memcpy(e.pos, literal, sizeof literal);
+    } else {
+        e.n = (uint32_t)(c->ent_pos.size() / 3);
+        std::memcpy(e.pos, c->ent_pos.data(), c->ent_pos.size() * sizeof(float));
+    }
+    return e;
+}
+
 ViewDev make_view(const uvt_ctx *c, uint32_t max_steps) {
     ViewDev v;
     v.W = c->W; v.H = c->H;
@@ -328,7 +354,9 @@ ViewDev make_view(const uvt_ctx *c, uint32_t max_steps) {
     v.map_dim = c->dim;
     v.max_steps = max_steps;
     v.epsilon = c->params.epsilon;
-    v.entities = (c->params.flags & UVT_FLAG_ENTITIES) ? 1u : 0u;
+    // the compiled-in test covers the reference as it runs (five literal boxes, map.glsl:199 returns); anything else
+    // is handled by the passes of entity.cuh after the traversal kernels
+    v.entities = ((c->params.flags & UVT_FLAG_ENTITIES) && !ent_custom(c)) ? 1u : 0u;
     return v;
 }
 
@@ -418,6 +446,24 @@ void launch_primary_pool(uvt_ctx *c, const ViewDev &v, const GBufDev &g) {
 #undef UVT_LAUNCH
 }
 
+// primary.comp.glsl:45-54 made live (uvt_set_entity_mode(UVT_ENTITY_MODELS)): the composite pass over `nrows` local rows from v.row0
+int launch_entity_primary(uvt_ctx *c, const ViewDev &v, const GBufDev &g, uint32_t nrows, uint32_t layers) {
+    if (c->ent_mode != UVT_ENTITY_MODELS || !(c->params.flags & UVT_FLAG_ENTITIES)) return UVT_OK;
+    UVT_REQUIRE(c, c->d_hit, "entity models need the hit buffer (uvt_set_entity_mode allocates it; uvt_resize after it)");
+    const dim3 grid((c->W + 63) / 64, (nrows + 3) / 4, layers);
+    if (layers > 1) entity_primary_kernel<true><<<grid, 256, 0, c->stream>>>(make_entities(c), c->d_cams, c->cam0, v, g);
+    else entity_primary_kernel<false><<<grid, 256, 0, c->stream>>>(make_entities(c), c->d_cams, c->cam0, v, g);
+    return check_launch(c, "entity_primary_kernel");
+}
+
+// secondary.comp.glsl:42-48 for an entity set the kernel's compiled-in literal test does not cover
+int launch_entity_shadow(uvt_ctx *c, const ViewDev &v, const GBufDev &g, uint32_t nrows, uint32_t layers) {
+    if (!ent_custom(c) || !(c->params.flags & UVT_FLAG_ENTITIES)) return UVT_OK;
+    const dim3 grid((c->W + 63) / 64, (nrows + 3) / 4, layers);
+    entity_shadow_kernel<<<grid, 256, 0, c->stream>>>(make_entities(c), v, g);
+    return check_launch(c, "entity_shadow_kernel");
+}
+
 template <int COUNT>
 int launch_primary(uvt_ctx *c) {
     const ViewDev v = make_view(c, c->params.primary_max_steps);
@@ -427,7 +473,9 @@ int launch_primary(uvt_ctx *c) {
     else if (COUNT != 1 && use_dense(c)) launch_primary_world<WorldDense, COUNT>(c, world_dense(c), v, g, grid);  // exact counters read the bricks
     else if (use_compact(c)) launch_primary_world<WorldCompact, COUNT>(c, world_compact(c), v, g, grid);
     else launch_primary_world<WorldRef, COUNT>(c, world_ref(c), v, g, grid);
-    return check_launch(c, "primary_kernel");
+    int rc = check_launch(c, "primary_kernel");
+    if (rc != UVT_OK) return rc;
+    return launch_entity_primary(c, v, g, storage_rows(c->H, c->band_rows, c->n_parts, c->part), c->layers);
 }
 
 // the sun clearance must cover the shadow step cap in force (it is built at commit time for the cap of that moment)
@@ -449,7 +497,9 @@ int launch_secondary(uvt_ctx *c) {
     else if (COUNT != 1 && use_dense(c)) secondary_kernel<WorldDense, COUNT><<<grid, kThreads, 0, c->stream>>>(world_dense(c), v, g, c->d_counters);
     else if (use_compact(c)) secondary_kernel<WorldCompact, COUNT><<<grid, kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
     else secondary_kernel<WorldRef, COUNT><<<grid, kThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
-    return check_launch(c, "secondary_kernel");
+    int rc = check_launch(c, "secondary_kernel");
+    if (rc != UVT_OK) return rc;
+    return launch_entity_shadow(c, v, g, storage_rows(c->H, c->band_rows, c->n_parts, c->part), c->layers);
 }
 
 // Build the B200 layout from the committed reference layout (all on the device):
@@ -705,7 +755,7 @@ void uvt_destroy(uvt_ctx *c) {
     cudaFree(c->d_rowmask); cudaFree(c->d_brick_chunk); cudaFree(c->d_tops32); cudaFree(c->d_scratch);
     cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]); cudaFree(c->d_clear64); cudaFree(c->d_clear16); cudaFree(c->d_sun4);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
-    cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame);
+    cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame); cudaFree(c->d_ent_model);
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 2; ++j)
             if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
@@ -1297,7 +1347,7 @@ int uvt_dispatch_frame(uvt_ctx *c) {
     const dim3 grid = trace_grid(c);
     const CamDev *cams = c->layers > 1 ? c->d_cams : nullptr;
     PassTimer t(c, 3);
-    if (use_pool(c) || !(c->params.flags & UVT_FLAG_FUSED_FRAME)) {
+    if (use_pool(c) || !(c->params.flags & UVT_FLAG_FUSED_FRAME) || ent_custom(c)) {
         // the three passes of game.zig:244-255 as three launches: measured faster than the fused kernel (c1 0.301 vs
         // 0.324 ms, c3 2.21 vs 2.41 ms) — the G-buffer round trip through L2 costs less than the registers and the
         // idle lanes of a kernel that keeps a primary and a shadow ray's state alive at once
@@ -1331,6 +1381,51 @@ int uvt_dispatch_frame(uvt_ctx *c) {
         else frame_kernel<WorldRef, true, false><<<grid, kThreads, 0, c->stream>>>(world_ref(c), cams, c->cam0, v, ss, g, ft);
     }
     return check_launch(c, "frame_kernel");
+}
+
+// ---- entities -----------------------------------------------------------------------------------
+int uvt_set_entity_mode(uvt_ctx *c, uint32_t mode) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_REQUIRE(c, mode == UVT_ENTITY_BOXES || mode == UVT_ENTITY_MODELS, "entity mode out of range");
+    c->ent_mode = mode;
+    if (mode == UVT_ENTITY_MODELS && !(c->params.flags & UVT_FLAG_HIT_BUFFER)) {
+        // the composite reads distance(C_position, inter.hit_pos / 8) (primary.comp.glsl:47) from the hit buffer
+        c->params.flags |= UVT_FLAG_HIT_BUFFER;
+        if (c->W && c->H) {
+            UVT_CUDA(c, cudaStreamSynchronize(c->stream));
+            return alloc_gbuffer(c);
+        }
+    }
+    return UVT_OK;
+}
+
+int uvt_set_entities(uvt_ctx *c, const float *positions_xyz, uint32_t n) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_REQUIRE(c, n <= (uint32_t)kMaxEntities, "at most 32 entities");
+    UVT_REQUIRE(c, n == 0 || positions_xyz, "positions is NULL");
+    if (n == 0) c->ent_pos.clear();  // back to the literal positions of map.glsl:173-179
+    else c->ent_pos.assign(positions_xyz, positions_xyz + 3 * (size_t)n);
+    return UVT_OK;
+}
+
+int uvt_entity_model_upload(uvt_ctx *c, uint32_t size, const uint32_t *rgba, uint32_t max_steps) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_CUDA(c, cudaStreamSynchronize(c->stream));  // a frame in flight may still read the old model
+    cudaFree(c->d_ent_model);
+    c->d_ent_model = nullptr;
+    c->ent_size = 8;
+    c->ent_steps = max_steps ? max_steps : 64u;
+    UVT_REQUIRE(c, c->ent_steps <= 65535u, "entity step cap above 65535");
+    if (!rgba) return UVT_OK;  // back to the atlas texels [0,8)^3
+    UVT_REQUIRE(c, size == 8 || size == 16 || size == 32, "entity model edge must be 8, 16 or 32 voxels");
+    const size_t bytes = (size_t)size * size * size * 4;
+    UVT_CUDA(c, cudaMalloc(&c->d_ent_model, bytes));
+    UVT_CUDA(c, cudaMemcpy(c->d_ent_model, rgba, bytes, cudaMemcpyHostToDevice));
+    c->ent_size = size;
+    return UVT_OK;
 }
 
 int uvt_pick(uvt_ctx *c, uvt_hit *out) {
@@ -1740,12 +1835,14 @@ int launch_rows(uvt_ctx *c, uint32_t row0, uint32_t nrows) {
     else if (use_compact(c)) launch_primary_world<WorldCompact, 0>(c, world_compact(c), v, g, grid);
     else launch_primary_world<WorldRef, 0>(c, world_ref(c), v, g, grid);
     int rc = check_launch(c, "primary_kernel");
+    if (rc == UVT_OK) rc = launch_entity_primary(c, v, g, nrows, 1);
     if (rc != UVT_OK) return rc;
     v.max_steps = c->params.shadow_max_steps;
     if (use_dense(c)) secondary_kernel<WorldDense, 0><<<grid, kThreads, 0, c->stream>>>(world_dense(c), v, g, c->d_counters);
     else if (use_compact(c)) secondary_kernel<WorldCompact, 0><<<grid, kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
     else secondary_kernel<WorldRef, 0><<<grid, kThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
     rc = check_launch(c, "secondary_kernel");
+    if (rc == UVT_OK) rc = launch_entity_shadow(c, v, g, nrows, 1);
     if (rc != UVT_OK) return rc;
     shade_kernel<<<dim3((c->W + 63) / 64, (nrows + 3) / 4, 1), 256, 0, c->stream>>>(v, g, make_target(c));
     return check_launch(c, "shade_kernel");

@@ -157,6 +157,29 @@ class Context:
     def sync(self):
         self.check(self.L.uvt_sync(self.handle))
 
+    def set_entity_mode(self, mode):
+        """traceEntities (map.glsl:172-248): "boxes" = the reference as it runs (returns at :199), "models" = the sub-model
+        DDA behind that return + the primary-pass composite of primary.comp.glsl:45-54 (turns the hit buffer on)."""
+        self.check(self.L.uvt_set_entity_mode(self.handle, {"boxes": N.UVT_ENTITY_BOXES, "models": N.UVT_ENTITY_MODELS}[mode]))
+
+    def set_entities(self, positions=None):
+        """`positions[]` of map.glsl:173-179 (low box corners, blocks); None restores the five literals."""
+        if positions is None:
+            self.check(self.L.uvt_set_entities(self.handle, None, 0))
+            return
+        p = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        self.check(self.L.uvt_set_entities(self.handle, p.ctypes.data, len(p)))
+
+    def entity_model_upload(self, model=None, size=8, max_steps=0):
+        """size^3 RGBA8 texels [z][y][x] (8, 16 or 32: chicken.vox); None = texels [0,8)^3 of the atlas (map.glsl:218)."""
+        if model is None:
+            self.check(self.L.uvt_entity_model_upload(self.handle, 8, None, int(max_steps)))
+            return
+        m = np.ascontiguousarray(model, dtype=np.uint32).reshape(-1)
+        if m.size != size ** 3:
+            raise ValueError("model must hold size^3 texels")
+        self.check(self.L.uvt_entity_model_upload(self.handle, int(size), m.ctypes.data, int(max_steps)))
+
     def pick(self):
         out = np.zeros((), dtype=N.HIT_DTYPE)
         self.check(self.L.uvt_pick(self.handle, out.ctypes.data))
@@ -366,6 +389,23 @@ class Group:
         buf = np.ascontiguousarray(cam)
         assert buf.nbytes == 96
         self.check(self.L.uvt_group_set_camera(self.handle, buf.ctypes.data))
+
+    def set_entity_mode(self, mode):
+        self.check(self.L.uvt_group_set_entity_mode(self.handle, {"boxes": N.UVT_ENTITY_BOXES, "models": N.UVT_ENTITY_MODELS}[mode]))
+
+    def set_entities(self, positions=None):
+        if positions is None:
+            self.check(self.L.uvt_group_set_entities(self.handle, None, 0))
+            return
+        p = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        self.check(self.L.uvt_group_set_entities(self.handle, p.ctypes.data, len(p)))
+
+    def entity_model_upload(self, model=None, size=8, max_steps=0):
+        if model is None:
+            self.check(self.L.uvt_group_entity_model_upload(self.handle, 8, None, int(max_steps)))
+            return
+        m = np.ascontiguousarray(model, dtype=np.uint32).reshape(-1)
+        self.check(self.L.uvt_group_entity_model_upload(self.handle, int(size), m.ctypes.data, int(max_steps)))
 
     def resize(self, w, h):
         self.check(self.L.uvt_group_resize(self.handle, w, h))

@@ -196,3 +196,23 @@ def parse_vox(data):
         return models, pal
     finally:
         L.uvt_vox_free(h)
+
+
+def load_model(data, size):
+    """The call src/game.zig:114 keeps commented out — `models.load_model("assets/chicken.vox", allocator, 32)` — for
+    the entity model of uvt_entity_model_upload: the first model of a .vox file as [size^3] RGBA8 texels indexed
+    x + size * (y + size * z), converted like load_single_block_model (voxel.zig:104-108: .vox z is up, so y and z
+    swap; colour = palette[index - 1]).  `data` is a path or the bytes of the file."""
+    if not isinstance(data, (bytes, bytearray)):
+        with open(data, "rb") as f:
+            data = f.read()
+    models, pal = parse_vox(data)
+    if not models:
+        raise UvtError(N.UVT_ERR_FORMAT, "no model in the .vox file")
+    (sx, sy, sz), vox = models[0]
+    if max(sx, sy, sz) > size:
+        raise UvtError(N.UVT_ERR_FORMAT, f"model is {sx}x{sy}x{sz}, larger than {size}^3")
+    out = np.zeros(size ** 3, dtype=np.uint32)
+    v = vox.astype(np.int64)
+    out[v[:, 0] + size * (v[:, 2] + size * v[:, 1])] = pal[(v[:, 3] - 1) & 255]
+    return out
