@@ -17,7 +17,7 @@ JSON line carries `also`: the 8K tiled frame (configs[3]) and the 1080p primary-
              counters from the counting variant of the same kernel) / measured kernel time.
   cpu_baseline  the CPU oracle (port of the reference GLSL) on this box's host cores, rank 0, N=1.
 
-N > 1 (torchrun): the world is replicated and the SAME frame is cut into interleaved 32-row bands
+N > 1 (torchrun): the world is replicated and the SAME frame is cut into interleaved 16-row bands
 across the ranks (strong scaling); the band exchange is inside the timed region: every rank's shade
 kernel stores its finished pixels straight into the presenting rank's frame over NVLink (--gather
 p2p, default) or the bands are gathered with NCCL (--gather nccl).  c2 at N > 1 runs one independent
@@ -44,7 +44,7 @@ WORKLOADS = {
     "c1": (512, 1280, 720, True, "c1: W1 procgen(512) world, camera K0, 1280x720, primary + shadow rays + shade"),
     "c2": (512, 1920, 1080, False, "c2: W1 procgen(512) world, camera K0, 1920x1080, primary rays only"),
     "c3": (2048, 3840, 2160, True, "c3: W4 procgen(2048) world, camera K1, 3840x2160, primary + shadow rays + shade (the 4K frame)"),
-    "c4": (512, 7680, 4320, True, "c4: W1 world, camera K1, 7680x4320 tiled in interleaved 32-row bands across ranks, bands assembled on rank 0"),
+    "c4": (512, 7680, 4320, True, "c4: W1 world, camera K1, 7680x4320 tiled in interleaved row bands across ranks, bands assembled on rank 0"),
     "c5": (2048, 1920, 1080, False, "c5: W4 world, 256 random poses at 1920x1080 sharded across ranks, primary rays"),
 }
 
@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="tiled frames: p2p = kernels store finished bands straight into rank 0's frame over NVLink (CUDA IPC peer mapping); "
                          "nccl = uvt_dispatch_frame_nccl: grouped ncclSend/ncclRecv per band group on a second stream, overlapped with the traversal of the next group")
+    ap.add_argument("--band-rows", type=int, default=16, help="rows per band of a tiled frame (a multiple of 16); 16 keeps the ranks' row counts within 1 %% of each other at 4K / 8 ranks")
     ap.add_argument("--nccl-groups", type=int, default=4, help="band groups per rank of the NCCL exchange (1 = exchange after the whole frame)")
     return ap.parse_args()
 
@@ -76,53 +77,135 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  Sampled through NVML
+    from a thread of this process every 2 ms — a timed region of a few tens of ms still gets samples, which an
+    `nvidia-smi -lms` child (slow to start) does not guarantee; nvidia-smi is the fallback when NVML is missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
+        self.samples = []   # (t, sm_mhz, reason mask)
+        self.sm_max = None
+        self.t0 = self.t1 = None
+        self.stop_flag = False
+        self.thread = None
+        self.source = None
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            reasons_fn(h)
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons_fn(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+            self.source = "nvidia-smi"
         except OSError:
             self.proc = None
 
     def _read(self):
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                mask = 0
+                for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        mask |= names[n]
+                self.samples.append((time.perf_counter(), float(f[1]), mask))
+                self.sm_max = max(self.sm_max or 0.0, float(f[2]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
+        time.sleep(0.01)
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e300)]
+        window = "timed region"
+        if not inside:  # a region shorter than the sampling period: the samples of the whole run under load (warm-up included)
+            inside, window = list(self.samples), "whole run (timed region shorter than the sampling period)"
+        mask = 0
+        for x in inside:
+            mask |= x[2]
+        sm = [x[1] for x in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(n for b, n in self.REASONS.items() if mask & b),
+                "samples": len(sm), "window": window, "source": self.source}
+
+
+class NvlinkCounters:
+    """NVLink data bytes received / sent by every GPU of the box (NVML field values
+    NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX / _TX, KiB, summed over the links): read before and after the timed region
+    on rank 0, this is the counter evidence for what the band exchange moves."""
+
+    def __init__(self, n):
+        self.n, self.ok, self.err = n, False, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in range(n)]
+            self.read()
+            self.ok = True
+        except Exception as e:  # no NVML / no NVLink counters in this container: reported, not fatal
+            self.err = f"{type(e).__name__}: {e}"
+
+    def read(self):
+        nv = self.nv
+        out = []
+        for h in self.handles:
+            vals = nv.nvmlDeviceGetFieldValues(h, [(nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF), (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF)])
+            row = []
+            for v in vals:
+                if v.nvmlReturn != 0:
+                    raise RuntimeError(f"NVML field {v.fieldId}: return {v.nvmlReturn}")
+                row.append(int(v.value.ullVal) * 1024)
+            out.append(row)
+        return out
+
+    @staticmethod
+    def delta(a, b):
+        return [[y - x for x, y in zip(ra, rb)] for ra, rb in zip(a, b)]
 
 
 def load_models():
@@ -249,7 +332,7 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
     dim, W, H, shadows, desc = WORKLOADS[workload]
     sweep = workload == "c5"
     tiled = world > 1 and workload in ("c1", "c3", "c4")   # one frame cut into bands across the ranks (strong scaling)
-    band = 32
+    band = args.band_rows
 
     ctx = uvt.Context(local_rank, map_dim=dim, layout=args.layout, dense=not args.no_dense, fused_frame=args.fused_frame)
     ctx.set_scheduler(args.scheduler)
@@ -323,15 +406,18 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
         alg_step += 4 * (cs["t_in"] + cs["t_chunk"] + cs["t_block"]) + 24 * cs["rays"] + 20 * cs["early_out"] + 32 * cp["rays"]
         rays_step += cs["rays"]
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(warmup):
         device_step(i)
     D.barrier()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    nvl = NvlinkCounters(world) if (tiled and rank == 0) else None
     launches0 = ctx.launch_count()
     step_ms, primary_ms = [], []
     D.barrier()
+    nvl0 = nvl.read() if (nvl and nvl.ok) else None
+    sampler.begin()
     wall0 = time.perf_counter()
     for i in range(steps):
         if flush is not None:
@@ -342,6 +428,8 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
         primary_ms.append(pm)
     D.barrier()
     wall = time.perf_counter() - wall0
+    sampler.end()
+    nvl1 = nvl.read() if (nvl and nvl.ok) else None
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop()
 
@@ -448,7 +536,7 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max([c.get("sm_max_mhz") or 0 for c in all_clocks]) or None,
                        "reasons": reasons, "samples": int(sum(c.get("samples", 0) for c in all_clocks)),
-                       "per_rank_sm_mhz": [c.get("sm_mhz") for c in all_clocks]},
+                       "per_rank_sm_mhz": [c.get("sm_mhz") for c in all_clocks], "window": all_clocks[0].get("window"), "source": all_clocks[0].get("source")},
             "roofline": {"bound": "l2", "kernel": "primary_kernel (the dominant launch of the step)", "achieved": achieved, "peak": l2_gbps, "unit": "GB/s",
                          "frac": achieved / l2_gbps, "traffic": ncu_traffic(workload),
                          "peak_source": "L2 read bandwidth measured in this run (16-B ld.global.cg over a 32 MiB resident buffer); MEASURED_PEAKS.json has no L2 figure",
@@ -467,6 +555,17 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
                                                      "ncclSend/ncclRecv on a second stream while the next group is traversed; inside the timed region" % args.nccl_groups)
             if verified is not None:
                 rec["config"]["frame_equals_torch_gather"] = verified
+            if nvl is not None:
+                if nvl0 is not None:
+                    d = NvlinkCounters.delta(nvl0, nvl1)
+                    expect = W * H * 4 * (world - 1) / world
+                    rec["nvlink"] = {"source": "NVML NVLINK_THROUGHPUT_DATA_RX/TX field values (KiB granularity), all links of each GPU, read on rank 0 around the timed steps",
+                                     "rx_bytes_per_step": [round(r[0] / steps) for r in d], "tx_bytes_per_step": [round(r[1] / steps) for r in d],
+                                     "expected_rank0_rx_bytes_per_step": round(expect),
+                                     "rank0_rx_over_expected": round(d[0][0] / steps / expect, 4) if expect else None,
+                                     "note": "expected = the (N-1)/N of the RGBA8 frame that the other ranks' bands hold (payload); the counters also see whatever else crosses NVLink in the timed region (the per-step barrier-free loop has no other traffic; NCCL adds its protocol)"}
+                else:
+                    rec["nvlink"] = {"unavailable": nvl.err}
             if e2e_ok is not None:
                 rec["e2e"]["host_frame_equals_device_frame"] = e2e_ok
         if want_cpu_baseline:
@@ -504,7 +603,7 @@ def run_ours(args):
         for wl, st in (("c4", max(30, min(args.steps, 60))), ("c2", args.steps)):
             r = measure(uvt, torch, D, args, wl, st, args.warmup, models, None, want_cpu_baseline=False)
             if r:
-                also[wl] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "e2e", "roofline", "gpu_launches") if k in r}
+                also[wl] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "scaling", "e2e", "roofline", "gpu_launches", "nvlink") if k in r}
                 also[wl]["workload"] = r["config"]["workload"]
                 also[wl]["parallelism"] = r["config"]["parallelism"]
                 if "pass_ms" in r:

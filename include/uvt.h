@@ -301,7 +301,7 @@ int  uvt_dispatch_frame_nccl(uvt_ctx *ctx, void *full_frame, uint32_t n_groups);
 
 /* ---- several GPUs in ONE process (the reference is a single-process game, src/game.zig) ----------
  * A group owns one ctx per device.  World and atlas are replicated from one pinned staging; the frame is cut into
- * interleaved 32-row bands (member i renders bands i, i+n, ...) and every member's kernels store their finished
+ * interleaved 16-row bands (member i renders bands i, i+n, ...) and every member's kernels store their finished
  * bands straight into the frame of member 0 over NVLink (peer access) — no gather pass.  Calls mirror the ctx calls
  * and fan out to every member; uvt_group_member(g, 0) presents (uvt_pick, timing, ...).  With n = 1 the group is a
  * plain ctx.  Only the FRAME is assembled; the G-buffers stay partitioned on their devices. */

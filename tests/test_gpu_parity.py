@@ -468,10 +468,10 @@ def test_c1_c2_bench_frames_full_size(uvt, oracle, w1, size):
 
 
 def test_c4_8k_frame_tiled_full_size(uvt, oracle, w1):
-    """BASELINE config 4: the 7680x4320 frame of W1 / K1 rendered as 8 interleaved 32-row band partitions (what 8 ranks render),
+    """BASELINE config 4: the 7680x4320 frame of W1 / K1 rendered as 8 interleaved 16-row band partitions (what 8 ranks render),
     assembled, and every one of its 33 M pixels compared with the oracle: hit records, G-buffer, illumination, shaded frame."""
     ctx, sc = w1
-    W, H, band, n_parts = 7680, 4320, 32, 8
+    W, H, band, n_parts = 7680, 4320, 16, 8
     cam = camera_k1(uvt, oracle)
     ctx.set_layout("compact")
     r = oracle.render(sc.oracle_world, cam, W, H)

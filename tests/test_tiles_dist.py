@@ -56,7 +56,7 @@ def test_gather_and_assemble_two_ranks(tmp_path, H, W, band):
     assert np.array_equal(frame, np.arange(H * W, dtype=np.int32).reshape(H, W))
 
 
-@pytest.mark.parametrize("H,band,n", [(1080, 32, 8), (4320, 32, 8), (100, 8, 3), (7, 8, 4), (64, 8, 1)])
+@pytest.mark.parametrize("H,band,n", [(1080, 32, 8), (4320, 32, 8), (2160, 16, 8), (4320, 16, 8), (100, 8, 3), (7, 8, 4), (64, 8, 1)])
 def test_partition_covers_every_row_exactly_once(uvt, H, band, n):
     t = uvt.tiles
     seen = np.zeros(H, np.int32)

@@ -2,7 +2,7 @@
 //
 // The reference is a single-process game (src/game.zig): its renderer cannot be launched one rank per GPU.
 // A group owns one uvt_ctx per device.  The world and the atlas are replicated (one pinned host staging, committed to
-// every member), the frame is cut into interleaved 32-row bands (member i renders bands i, i+n, ...) and
+// every member), the frame is cut into interleaved 16-row bands (member i renders bands i, i+n, ...) and
 // every member's kernels store their finished bands straight into the frame of member 0 through peer access — the
 // same fused compute + "gather" the torchrun path uses with CUDA IPC, without a second process.
 //
@@ -27,7 +27,7 @@ struct uvt_group {
 
 namespace {
 
-constexpr uint32_t kBandRows = 32;
+constexpr uint32_t kBandRows = 16;  // two CTA tile rows; 2160 rows over 8 members: 272 vs 256-288 rows with 32-row bands
 std::string g_group_create_error;
 
 int group_error(uvt_group *g, int code, const char *fmt, ...) {

@@ -343,7 +343,7 @@ def init(device=0, **kw):
 
 class Group:
     """Several GPUs behind one handle in ONE process (uvt_group, include/uvt.h): world and atlas replicated, the frame
-    cut into interleaved 32-row bands, every member storing its bands into member 0's frame over NVLink."""
+    cut into interleaved 16-row bands, every member storing its bands into member 0's frame over NVLink."""
 
     is_group = True
 
