@@ -228,36 +228,63 @@ def ncu_traffic(workload):
 
 
 # ------------------------------------------------------------------------------------------------
+def reference_cpu():
+    """The reference's CPU implementation of the path: its own shader text compiled for the host (oracle/_ref/libglslref.so,
+    kind "reference") when that library is here, else the oracle port (kind "port").  Returns (kind, render(world, cam, W, H, shadows)
+    -> rays traced, threads, note)."""
+    import oracle
+    n = os.cpu_count() or 1
+    try:
+        from oracle import glslref
+        ok = glslref.available()
+    except Exception:
+        ok = False
+    if ok:
+        glslref.lib()
+        glslref.set_num_threads(n)  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread
+
+        def render(world, cam, W, H, shadows):
+            if shadows:
+                r = glslref.render(world, cam, W, H)
+                return W * H + glslref.shadow_rays(r["position"])
+            glslref.primary(world, cam, W, H)
+            return W * H
+        return "reference", render, glslref.num_threads(), ("the reference's own GLSL (assets/shaders/primary.comp, secondary.comp, blit.fragment + includes) compiled for the "
+                                                            "CPU against a GLSL-in-C++ shim (oracle/glsl_ref), OpenMP over work groups; the GL program itself cannot run in this image")
+    oracle.set_num_threads(n)
+    prm_cache = {}
+
+    def render(world, cam, W, H, shadows):
+        prm = prm_cache.setdefault(world.dim, oracle.params(world.dim))
+        if shadows:
+            r = oracle.render(world, cam, W, H, prm, want_hits=False)
+            return W * H + r["secondary_counters"]["rays"]
+        oracle.primary(world, cam, W, H, prm, want_hits=False)
+        return W * H
+    return "port", render, oracle.num_threads(), "CPU restatement of the reference GLSL (oracle/oracle.c); oracle/_ref is not built here"
+
+
 def run_reference(args):
-    """The reference's own CPU implementation of the path: the oracle port (OpenMP over rows, all host
-    threads).  The real reference is GLSL on OpenGL and cannot run in this image."""
+    """The reference's own CPU implementation of the path on the box's host cores, all threads, on a bounded sample of the
+    same workload.  The real reference is GLSL on OpenGL and cannot run in this image; its shader text can (oracle/_ref)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     import oracle
-    oracle.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread
+    kind, render, threads, note = reference_cpu()
     uvt = importlib.import_module("unnamed-voxel-tracer_b200")
     dim, W, H, shadows, desc = WORKLOADS[args.workload]
-    if args.workload in ("c3", "c4", "c5"):
-        # bounded sample: these frames are minutes of CPU work; time a 1/16-area frame and scale per ray
-        scale = 4
-    else:
-        scale = 1
+    # bounded sample: the 4K / 8K / sweep frames are seconds of CPU work each; time a 1/16-area frame and scale per ray
+    scale = 4 if args.workload in ("c3", "c4", "c5") else 1
     Ws, Hs = W // scale, H // scale
     bm = uvt.voxel.VoxelBrickmap.init(dim)
     uvt.procgen.procgen(dim, bm)
     ow = oracle.World(dim, bm.chunks(), bm.bricks(), oracle.atlas_from_models(load_models()))
     cam = uvt.scenes.camera_k0(dim) if args.workload in ("c1", "c2") else uvt.scenes.camera_k1(dim)
-    prm = oracle.params(dim)
 
     def step():
         t0 = time.perf_counter()
-        if shadows:
-            r = oracle.render(ow, cam, Ws, Hs, prm, want_hits=False)
-            rays = Ws * Hs + r["secondary_counters"]["rays"]
-        else:
-            oracle.primary(ow, cam, Ws, Hs, prm, want_hits=False)
-            rays = Ws * Hs
+        rays = render(ow, cam, Ws, Hs, shadows)
         return time.perf_counter() - t0, rays
 
     for _ in range(max(1, min(args.warmup, 1))):
@@ -274,10 +301,9 @@ def run_reference(args):
             "scaling": "strong" if (args.gpus > 1 and args.workload in ("c1", "c3", "c4")) else "weak",
             "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic (procgen world, reference seeds)",
             "config": {"workload": desc, "rays_per_step": rays * scale * scale, "cpu_sample": sample},
-            "cpu_baseline": {"value": value, "unit": "Grays/s", "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "Grays/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Grays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-            "note": "CPU restatement of the reference GLSL (oracle/oracle.c); Mesa llvmpipe / Zig / GL are not available in this image"}
+            "gpu_launches": 0, "note": note}
     print(json.dumps(line))
 
 
@@ -619,27 +645,22 @@ def run_ours(args):
 
 
 def cpu_baseline(uvt, bm, dim, W, H, shadows, cam, models):
-    """The oracle (CPU port of the reference GLSL) on this box's host cores: bounded sample of the same workload."""
+    """The reference's CPU implementation (its own shader text compiled for the host when oracle/_ref is here, else the
+    oracle port) on this box's host cores: a bounded sample of the same workload."""
     import oracle
-    oracle.set_num_threads(os.cpu_count() or 1)
+    kind, render, threads, note = reference_cpu()
     scale = 1 if W * H <= 1920 * 1080 and dim <= 512 else 4
     Ws, Hs = W // scale, H // scale
     ow = oracle.World(dim, bm.chunks(), bm.bricks(), oracle.atlas_from_models(models))
-    prm = oracle.params(dim)
     best, rays = None, 0
     for _ in range(3):
         t0 = time.perf_counter()
-        if shadows:
-            r = oracle.render(ow, cam, Ws, Hs, prm, want_hits=False)
-            rays = Ws * Hs + r["secondary_counters"]["rays"]
-        else:
-            oracle.primary(ow, cam, Ws, Hs, prm, want_hits=False)
-            rays = Ws * Hs
+        rays = render(ow, cam, Ws, Hs, shadows)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": rays / best / 1e9, "unit": "Grays/s", "cores": oracle.num_threads(), "kind": "port",
-            "sample": f"{Ws}x{Hs} frame of the same workload ({'full size' if scale == 1 else '1/%d of the pixels' % (scale * scale)}), best of 3, OpenMP over rows",
-            "ms_per_frame_sample": best * 1e3}
+    return {"value": rays / best / 1e9, "unit": "Grays/s", "cores": threads, "kind": kind,
+            "sample": f"{Ws}x{Hs} frame of the same workload ({'full size' if scale == 1 else '1/%d of the pixels' % (scale * scale)}), best of 3, OpenMP",
+            "ms_per_frame_sample": best * 1e3, "what": note}
 
 
 if __name__ == "__main__":

@@ -1226,3 +1226,70 @@ def test_entity_models_with_every_dispatch_path(uvt, oracle, scene_factory):
             full[rows] = f.reshape(-1, W)[:len(rows)]
             kinds[rows] = h.reshape(-1, W)[:len(rows)]["exit_kind"]
         assert channel_diff(full, r["frame"]).max() <= 1 and np.array_equal(kinds, r["hits"]["exit_kind"])
+
+
+# ---- the CUDA path against the reference's OWN shader text (oracle/_ref/libglslref.so, oracle/glsl_ref/) ------------------
+def assert_gbuffer_equals_reference_text(g, ref):
+    """ref: images produced by the reference's shader text.  Hits (position.w == 1) bit-exact in every image; sky albedo and
+    the shaded frame within 1/255 (integer powers by multiplication vs powf)."""
+    hit = ref["position"][..., 3] == 1.0
+    assert np.array_equal(g["normal"], ref["normal"])
+    assert np.array_equal(g["position"].view(np.uint32), ref["position"].view(np.uint32))
+    assert np.array_equal(g["illumination"], ref["illumination"])
+    assert np.array_equal(g["albedo"][hit], ref["albedo"][hit])
+    assert channel_diff(g["albedo"], ref["albedo"]).max() <= 1
+    assert channel_diff(g["frame"], ref["frame"]).max() <= 1
+    return int(hit.sum())
+
+
+def test_committed_reference_shader_golden(uvt, oracle, w1):
+    """tests/golden/glslref_w1_*.npz: outputs of the reference's shader text (made in the build container by
+    tools/make_golden.py, reproduced there by tests/test_glsl_reference.py) against the GPU."""
+    import os
+    from conftest import GOLDEN
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    ctx.resize(96, 54)
+    for name in ("k0_96x54", "k1_96x54"):
+        gold = np.load(os.path.join(GOLDEN, f"glslref_w1_{name}.npz"))
+        cam = np.frombuffer(gold["camera"].tobytes(), dtype=oracle.CAMERA_DTYPE)[0]
+        assert assert_gbuffer_equals_reference_text(gpu_render(ctx, cam), gold) > 2000
+
+
+@pytest.mark.parametrize("size", [(1280, 720), (1920, 1080)])
+def test_gpu_equals_the_reference_shader_text_full_size(uvt, oracle, w1, size):
+    """BASELINE configs 1 and 2 at full size: every G-buffer image, the illumination image and the frame of the CUDA path
+    against the reference's own GLSL compiled for the CPU (the prebuilt oracle/_ref library travels to the GPU box)."""
+    from oracle import glslref
+    if not glslref.available():
+        pytest.skip("oracle/_ref/libglslref.so is not here")
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    W, H = size
+    ctx.resize(W, H)
+    for cam in (camera_k0(oracle), camera_k1(uvt, oracle)):
+        ref = glslref.render(sc.oracle_world, cam, W, H)
+        assert assert_gbuffer_equals_reference_text(gpu_render(ctx, cam), ref) > W * H // 3
+
+
+def test_gpu_equals_the_reference_shader_text_w4_and_entities(uvt, oracle, w4, w1):
+    from oracle import glslref
+    if not glslref.available() or not glslref.available("entities"):
+        pytest.skip("oracle/_ref is not here")
+    ctx, sc = w4
+    W, H = 960, 540
+    ctx.resize(W, H)
+    for cam in (uvt.scenes.camera_k1(2048), uvt.scenes.sweep_poses(2048, 6)[5]):
+        assert assert_gbuffer_equals_reference_text(gpu_render(ctx, cam), glslref.render(sc.oracle_world, cam, W, H)) > W * H // 5
+    # SURVEY 8 f3 against the dead code made live (map.glsl:199 deleted, primary.comp.glsl:47-54 uncommented)
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    ctx.resize(320, 180)
+    try:
+        ctx.set_entity_mode("models")
+        ctx.resize(320, 180)
+        for p, pitch, yaw in ENTITY_CAMERAS:
+            cam = oracle.make_camera(p, pitch_yaw_matrix(uvt, pitch, yaw))
+            assert_gbuffer_equals_reference_text(gpu_render(ctx, cam), glslref.render(sc.oracle_world, cam, 320, 180, variant="entities"))
+    finally:
+        ctx.set_entity_mode("boxes")

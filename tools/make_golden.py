@@ -7,6 +7,8 @@
   atlas_counts.json  filled sub-voxels per model (cross-checked against SURVEY App. B.3).
   chicken_32.npy     [32768] u32 — assets/chicken.vox (the entity model of src/game.zig:114) as 32^3 texels, x + 32*(y + 32*z),
                      converted by voxel.load_model (same y/z swap and palette rule as the block models).
+  glslref_*.npz      outputs of the REFERENCE'S OWN shader text (oracle/_ref/libglslref.so = assets/shaders/*.glsl compiled for the
+                     CPU, oracle/glsl_ref/): G-buffer images, illumination and final frame of the same small fixed scenes.
   oracle_*.npz       oracle outputs for small fixed scenes (hit buffers, G-buffers, frame, counters).
 """
 import importlib
@@ -61,6 +63,10 @@ def make_oracle_goldens():
                             primary_counters=np.array([pc[k] for k in ("rays", "t_in", "t_chunk", "t_block", "hits")], dtype=np.uint64),
                             camera=np.frombuffer(cam.tobytes(), np.float32))
         print(name, pc, r["secondary_counters"])
+        from oracle import glslref
+        g = glslref.render(world, cam, 96, 54)
+        np.savez_compressed(os.path.join(GOLD, f"glslref_w1_{name}.npz"), albedo=g["albedo"], normal=g["normal"], position=g["position"],
+                            illumination=g["illumination"], frame=g["frame"], camera=np.frombuffer(cam.tobytes(), np.float32))
 
 
 if __name__ == "__main__":

@@ -98,6 +98,13 @@ __device__ __forceinline__ bool trace_entities(float ox, float oy, float oz, flo
     float prev_d = __int_as_float(0x7f800000);
     bool any = false;
     const float dd = dx * dx + dy * dy + dz * dz;
+    {   // the five box centres lie within 3.91 blocks of (254.5, 21.5, 259): a line that passes that point by more than 5 blocks is
+        // more than 1.09 from every centre, so the per-box rejection below (distance > 1) would drop all five — which is
+        // every shadow ray of a frame that looks somewhere else
+        const float vx = 254.5f - ox, vy = 21.5f - oy, vz = 259.0f - oz;
+        const float cx = vy * dz - vz * dy, cy = vz * dx - vx * dz, cz = vx * dy - vy * dx;
+        if (cx * cx + cy * cy + cz * cz > 25.0f * dd) return false;
+    }
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         {   // A line further than 1 block from the box centre misses the unit box (half diagonal 0.866): its slab intervals are
