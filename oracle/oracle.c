@@ -5,13 +5,20 @@
  * this file; it is the parity checker for tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py.
  *
- * The reference is GLSL 4.50 compute + Zig/OpenGL host code and cannot be compiled or run in
- * this image (no Zig, no GL, no Mesa: SURVEY.md §8c), so there is no oracle/_ref build.  The
- * reference holds no golden vectors or known-answer tests for this path; the
- * restatement is pinned instead by (1) the hand-derived known answers of SURVEY App. A.7,
- * (2) an independent pure-Python restatement (oracle/pyref.py) written from the shader text,
- * and (3) committed golden fixtures produced by this oracle.  PARITY UNPINNED against a
- * running copy of the reference itself — stated here and in DESIGN.md.
+ * The reference is GLSL 4.50 compute + Zig/OpenGL host code and cannot be run as a program in
+ * this image (no Zig, no GL, no Mesa: SURVEY.md §8c), and it holds no golden vectors or
+ * known-answer tests for this path.  What pins this restatement:
+ * (1) oracle/_ref/libglslref.so — the reference's OWN shader text (assets/shaders/*.glsl, read
+ *     where it lies, translated by syntactic rewrites only and compiled for the CPU against a
+ *     GLSL-in-C++ shim: oracle/glsl_ref/).  tests/test_glsl_reference.py holds this file to it
+ *     bit for bit: every G-buffer image, the illumination image and the final frame, traceMap,
+ *     traceEntities and SkyDome2 ray by ray, on the default world, small worlds and the 4x world;
+ * (2) the hand-derived known answers of SURVEY App. A.7;
+ * (3) an independent pure-Python restatement (oracle/pyref.py) written from the shader text;
+ * (4) committed golden fixtures (tests/golden/: outputs of the reference text and of this file).
+ * Still unpinned: what a real GL driver does where GLSL leaves room (NaN handling of min/max/
+ * clamp, pow, rounding of normalize, UNORM conversion) — both sides follow the contract below —
+ * and the third-party noise / .vox code behind the INPUTS of the path.
  *
  * Every function cites the reference lines it follows (paths relative to the reference
  * checkout).  Arithmetic rules: fp32 everywhere, every + - * / individually
