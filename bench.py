@@ -610,7 +610,37 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
     ctx.close()
     del flush, gather_buf, full_frame
     torch.cuda.empty_cache()
+    if rec is not None and workload == "c2" and world == 1:
+        rec["e2e"]["hit_buffer"] = e2e_hit_buffer(uvt, local_rank, dim, W, H, cam, models, min(steps, 20))
     return rec
+
+
+def e2e_hit_buffer(uvt, device, dim, W, H, cam, models, steps):
+    """The same end-to-end loop when the step's result is the explicit 28 B/px HIT BUFFER (the north-star parity artefact:
+    hit voxel, face, material, distance, trips) instead of the 4 B/px image: the primary pass writes it (HITBUF variant)
+    and every frame's records are copied to pinned host memory.  PCIe-bound by construction."""
+    with uvt.Context(device, map_dim=dim, hit_buffer=True) as ctx:
+        uvt.scenes.build_world(ctx, dim, models)
+        ctx.resize(W, H)
+        ctx.set_camera(cam)
+        nbytes = W * H * 28
+        pinned = [ctx.pinned_empty(nbytes, np.uint8), ctx.pinned_empty(nbytes, np.uint8)]
+
+        def step(i):
+            ctx.set_camera(cam)
+            ctx.dispatch_primary()
+            ctx.readback_async("hit", pinned[i & 1])
+        for i in range(2):
+            step(i)
+        ctx.readback_wait()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step(i)
+        ctx.readback_wait()
+        dt = time.perf_counter() - t0
+    return {"value": W * H * steps / dt / 1e9, "unit": "Grays/s", "d2h_bytes_per_step": nbytes, "ms_per_step": dt / steps * 1e3, "steps": steps,
+            "d2h_gb_per_s": round(nbytes * steps / dt / 1e9, 2),
+            "what": "uvt_set_camera + primary pass with the hit buffer on + uvt_readback_async of the 28 B/px hit records into pinned host memory, pipelined like e2e.value"}
 
 
 def run_ours(args):

@@ -728,6 +728,11 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
 #endif
 
         // ---- k DDA steps, branch-free (map.glsl:157-162) -----------------------------------
+#ifdef UVT_DDA_UNROLL  // experiment knob (tools/variants.py); the default leaves the unrolling to the compiler (x4)
+#define UVT_PRAGMA_(x) _Pragma(#x)
+#define UVT_PRAGMA(x) UVT_PRAGMA_(x)
+        UVT_PRAGMA(unroll UVT_DDA_UNROLL)
+#endif
         for (int j = 1; j < k; ++j) dda_step(gx, gy, gz, wx, wy, wz, isx, isy, isz, tgx, tgy, tgz, invx, invy, invz, dx, dy, dz, rsx, rsy, rsz);
         {   // the last step of the run also reports minIdx: a hit in the next lookup needs it for the face id
             int mxi, myi;
