@@ -164,7 +164,8 @@ int  uvt_world_commit_region(uvt_ctx *ctx, size_t n_bricks, const uint32_t lo[3]
 int  uvt_world_set_voxel(uvt_ctx *ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t voxel, int *written);
 /* Checksums of the layout the commit derived (test hook: an incremental commit must leave exactly what a full
  * commit builds).  Keyed by block position, independent of brick numbering: out[0] dense grid, out[1] brick
- * view (brick bytes + far-empty chunk entries), out[2] column-group tops, out[3] = y_clear | n_materials << 32. */
+ * view (brick bytes + far-empty chunk entries), out[2] column-group tops + per-column tops and sun clearance, out[3] = y_clear |
+ * n_materials << 32. */
 int  uvt_world_layout_checksum(uvt_ctx *ctx, uint64_t out[4]);
 
 /* procgen on the device (src/procgen.zig:6-70): the world the serial host procgen (uvt_procgen, uvt_host.h)

@@ -1293,3 +1293,57 @@ def test_gpu_equals_the_reference_shader_text_w4_and_entities(uvt, oracle, w4, w
             assert_gbuffer_equals_reference_text(gpu_render(ctx, cam), glslref.render(sc.oracle_world, cam, 320, 180, variant="entities"))
     finally:
         ctx.set_entity_mode("boxes")
+
+
+# ---- the per-column sun clearance map (sun1): shadow rays sealed at their first lookup at or above it ---------------------
+def _sun_world(seed):
+    """Terrain that fights the sun clearance: stairs rising towards the sun (+x, +z), plateaus, thin slabs and pillars floating
+    a few blocks above the surface along the sun direction of the blocks under them."""
+    def fill(bm):
+        rng = np.random.default_rng(seed)
+        base = 8
+        for x in range(16, 112):
+            for z in range(16, 112):
+                h = base + ((x + z) // (3 + seed % 3)) % 7 + (2 if (x // 9 + z // 11) % 3 == 0 else 0)
+                for y in range(max(h - 2, 0), h):
+                    bm.set(x, y, z, WATER)
+        for _ in range(60):   # obstacles placed where SUN_DIR rays of nearby ground pass: (dx, dy, dz) ~ k * (0.75, 0.66, 0.75)
+            x, z = int(rng.integers(20, 100)), int(rng.integers(20, 100))
+            k = int(rng.integers(2, 14))
+            ox, oz, oy = x + int(round(0.75 * k)) + int(rng.integers(-1, 2)), z + int(round(0.75 * k)) + int(rng.integers(-1, 2)), base + 8 + int(round(0.66 * k)) + int(rng.integers(-2, 3))
+            for a in range(int(rng.integers(1, 4))):
+                for b in range(int(rng.integers(1, 4))):
+                    if ox + a < 126 and oz + b < 126:
+                        bm.set(ox + a, oy, oz + b, WATER)
+    return fill
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_sun_clearance_against_adversarial_terrain_and_step_caps(uvt, oracle, scene_factory, seed):
+    down = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, -1, 0, 0], [0, 0, 0, 1]], np.float32)
+    with uvt.Context(0, map_dim=128, hit_buffer=True) as ctx:
+        sc = scene_factory(128, _sun_world(seed), ctx=ctx)
+        W, H = 224, 160
+        ctx.resize(W, H)
+        cams = [oracle.make_camera((64.0, 60.0, 64.0), down, 1.6), oracle.make_camera((30.0, 40.0, 30.0), pitch_yaw_matrix(uvt, 0.7, np.pi / 4)),
+                oracle.make_camera((100.0, 35.0, 90.0), pitch_yaw_matrix(uvt, 0.5, 3.9))]
+        for shadow_cap in (48, 17, 96, 48):   # growing the cap rebuilds the map (ensure_sun); shrinking keeps the larger one
+            ctx.set_max_steps(192, shadow_cap)
+            prm = oracle.params(128, shadow_max_steps=shadow_cap)
+            for cam in cams:
+                g = gpu_render(ctx, cam)
+                r = oracle.render(sc.oracle_world, cam, W, H, prm)
+                assert np.array_equal(g["illumination"], r["illumination"]), (seed, shadow_cap)
+                assert len(np.unique(r["illumination"])) == 3 or (r["illumination"] != 0).any()
+                assert ctx.count_pass("secondary") == {**r["secondary_counters"]}
+        # a new obstacle far along the sun direction of lit ground, published incrementally: the map follows (update_sun)
+        for x, y, z in ((70, 30, 72), (71, 30, 72), (70, 31, 73), (90, 25, 88)):
+            sc.bm.set(x, y, z, WATER)
+        sc.bm.bind(9)
+        inc = ctx.world_layout_checksum()
+        world = oracle.World(128, sc.bm.chunks().copy(), sc.bm.bricks().copy(), oracle.atlas_from_models(sc.models))
+        for cam in cams:
+            assert np.array_equal(gpu_render(ctx, cam)["illumination"], oracle.render(world, cam, W, H)["illumination"])
+        sc.bm.mark_dirty()
+        sc.bm.bind(9)   # full commit of the same world
+        assert ctx.world_layout_checksum() == inc

@@ -707,36 +707,56 @@ __global__ void coarse_clear_kernel(const uint16_t *__restrict__ in, uint16_t *_
     out[i] = (uint16_t)m;
 }
 
-// Sun clearance of the shadow pass.  Every shadow ray has the direction SUN_DIR = (s, u, s), all components positive, so
-// what line_free_trips() would find for it depends only on where it starts.  For a ray whose state P lies in column group q:
-// the line runs along the diagonal of the x-z plane and enters group c = q + (a, b) (a, b >= 0, |a - b| <= 1) after an
-// x-advance of at least 4 * max(max(a, b) - 1, 0) blocks, i.e. a climb of at least that times u / s; travelling up every
-// axis the state is ON the line (no 0.999-reset drift), and a lookup names the line's block or, by the round-up carry, a
-// neighbour one block over: clear4 is grown by one block.  So with
-//     sun4[q] = max over the groups c within reach of  clear4[c] - (u / s) * 4 * max(max(a, b) - 1, 0)      (rounded up)
-// a state in a block row ABOVE sun4[q] looks up nothing but empty blocks for `steps` trips; groups beyond the x / z faces
-// make the value infinite (the ray could leave the map), the top face is the caller's sun_row_max.  Reach: `steps` trips
-// cover at most (steps + 5) / (2 s + u) of parameter, s times that along x.
-__global__ void sun_clear_kernel(const uint16_t *__restrict__ clear4, uint16_t *__restrict__ sun4, int qdim, int steps) {
+// Sun clearance of the shadow pass, per block column.  Every shadow ray has the direction SUN_DIR = (s, u, s), all components
+// positive, so how long it stays in open air depends only on where it starts.  Take a ray whose state lies in column (X, Z),
+// block row r.  Travelling up every axis the state never moves down or back: `within += dir * t` adds non-negative numbers and
+// a reset puts the stepped axis exactly on the face it reached, so in fp32, too, every later state has y >= the row's floor.
+// A lookup names the state's block or, when a `within` component has rounded up to the step size, the next one up that axis —
+// never a lower row, at most one column further.  The line runs along the diagonal of the x-z plane (s_x = s_z): it can only
+// visit columns (X + a, Z + b) with a, b >= 0 and |a - b| <= 1, and it is inside such a column only after an x- (or z-)
+// advance of more than max(a, b) - 1 blocks, i.e. after climbing (u / s) * max(max(a, b) - 1, 0) blocks (the real trajectory
+// follows the ideal line to ~1e-5 block over 48 trips; 0.01 block of the credit is given up for that).  Hence with
+//     top3[c]  = the highest column top (first all-empty row) over columns c + [-1, +2]^2   (carry + one column of drift)
+//     sun1[X,Z] = max over the reachable (a, b) of  ceil(top3[X + a, Z + b] - max((u / s) * max(max(a, b) - 1, 0) - 0.01, 0))
+// a state in a row >= sun1 looks up nothing but empty blocks for `steps` trips.  Columns beyond the x / z faces make the
+// value infinite (the ray could leave the map before the cap); the top face is the caller's sun_row_max.  Reach: `steps`
+// trips cover at most (steps + 5) / (2 s + u) of parameter, s times that along x.
+// (x0, z0)-(x1, z1): the rectangle of columns to (re)compute, inclusive — everything, or the surroundings of an edit.
+__global__ void top3_kernel(const unsigned int *__restrict__ tops32, uint16_t *__restrict__ top3, int dim, int x0, int z0, int x1, int z1) {
+    const int w = x1 - x0 + 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= qdim * qdim) return;
-    const int qx = i % qdim, qz = i / qdim;
-    const float reach_x = UVT_SUN_X * (float)(steps + 5) / (2.0f * UVT_SUN_X + UVT_SUN_Y);  // blocks along x (= along z)
-    const int K = (int)(reach_x * 0.25f) + 2;                                                // groups ahead that the line may reach
-    const float climb = UVT_SUN_Y / UVT_SUN_X * 4.0f;
-    float m = 0.0f;
+    if (i >= w * (z1 - z0 + 1)) return;
+    const int x = x0 + i % w, z = z0 + i / w;
+    unsigned int m = 0;
+    for (int zz = max(z - 1, 0); zz <= min(z + 2, dim - 1); ++zz)
+        for (int xx = max(x - 1, 0); xx <= min(x + 2, dim - 1); ++xx) m = max(m, tops32[(size_t)xx + (size_t)dim * zz]);
+    top3[(size_t)x + (size_t)dim * z] = (uint16_t)min(m, 0xFFFEu);
+}
+
+__host__ __device__ inline int sun_reach_columns(int steps) {
+    return (int)(UVT_SUN_X * (float)(steps + 5) / (2.0f * UVT_SUN_X + UVT_SUN_Y)) + 2;
+}
+
+__global__ void sun_clear_kernel(const uint16_t *__restrict__ top3, uint16_t *__restrict__ sun1, int dim, int steps, int x0, int z0, int x1, int z1) {
+    const int w = x1 - x0 + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * (z1 - z0 + 1)) return;
+    const int x = x0 + i % w, z = z0 + i / w;
+    const int K = sun_reach_columns(steps);
+    const float climb = UVT_SUN_Y / UVT_SUN_X;
+    int m = 0;
     bool open = false;
     for (int k = 0; k <= K; ++k) {
-        const float rise = climb * (float)max(k - 1, 0);
+        const float credit = fmaxf(climb * (float)max(k - 1, 0) - 0.01f, 0.0f);
         for (int j = 0; j < 3; ++j) {  // (a, b) = (k, k), (k, k - 1), (k - 1, k)
             const int a = j == 2 ? k - 1 : k, b = j == 1 ? k - 1 : k;
             if (a < 0 || b < 0) continue;
-            const int cx = qx + a, cz = qz + b;
-            if (cx >= qdim || cz >= qdim) { open = true; continue; }
-            m = fmaxf(m, (float)clear4[cx + qdim * cz] - rise);
+            const int cx = x + a, cz = z + b;
+            if (cx >= dim || cz >= dim) { open = true; continue; }
+            m = max(m, (int)ceilf((float)top3[(size_t)cx + (size_t)dim * cz] - credit));
         }
     }
-    sun4[i] = open ? (uint16_t)0xFFFF : (uint16_t)min((int)ceilf(m), 0xFFFE);
+    sun1[(size_t)x + (size_t)dim * z] = open ? (uint16_t)0xFFFF : (uint16_t)min(m, 0xFFFE);
 }
 
 // Block-level clearance.  One CTA per brick, one thread per block.  The occupancy of the 5x5x5 chunk
@@ -1000,9 +1020,10 @@ __global__ void __launch_bounds__(64) layout_checksum_kernel(const uint32_t *__r
     }
 }
 
-__global__ void clear4_checksum_kernel(const uint16_t *__restrict__ clear4, int n, unsigned long long *out) {
+// position-keyed checksum of a u16 map (clear4, top3, sun1: `salt` keeps them apart), added into out[2]
+__global__ void clear4_checksum_kernel(const uint16_t *__restrict__ clear4, int n, unsigned long long *out, unsigned long long salt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long h = i < n ? (unsigned long long)(clear4[i] + 1u) * (mix64((unsigned long long)i + 7ull) | 1ull) : 0ull;
+    unsigned long long h = i < n ? (unsigned long long)(clear4[i] + 1u) * (mix64((unsigned long long)i + salt) | 1ull) : 0ull;
     for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
     if ((threadIdx.x & 31u) == 0 && h) atomicAdd(out + 2, h);
 }

@@ -94,8 +94,8 @@ struct WorldCompact {
                                             // kMatLimit + min(n_free, 30)) without the chunk indirection; nullptr when not built
     const uint16_t *__restrict__ clear64;   // [ceil(dim/64)^2] maximum of clear4 over 64x64-block column groups (coarsest level of the walk)
     const uint16_t *__restrict__ clear16;   // [ceil(dim/16)^2] ... over 16x16-block column groups
-    const uint16_t *__restrict__ sun4;      // [(dim/4)^2] sun clearance: a SUN_DIR ray whose state lies in this column group, in a block row
-                                            // ABOVE this value, meets nothing but empty in-map blocks for sun_steps trips (sun_clear_kernel)
+    const uint16_t *__restrict__ sun1;      // [dim^2] sun clearance per block column: a SUN_DIR ray whose state lies in this column, in a block
+                                            // row AT OR ABOVE this value, meets nothing but empty in-map blocks for sun_steps trips (sun_clear_kernel)
     int32_t sun_row_max;                    // ... provided its block row is at most this (the ray stays under the top face)
     const uint16_t *__restrict__ clear4;    // [(dim/4)^2] per 4x4-block column group, grown by one block on every side:
                                             // every block with y >= clear4 there is empty (sky_sealed)
@@ -493,7 +493,7 @@ constexpr int kWalkGap = UVT_WALK_GAP;          // trips between the end of a pr
 constexpr int kWalkBackoffShift = UVT_WALK_BACKOFF_SHIFT;  // ... after a failed walk: max_steps >> this (48 of 192 trips)
 
 // Must be called by ALL 32 lanes of a warp (it uses full-mask warp reductions); `active` = this lane has a ray.
-// SUN: the direction is camera.glsl's SUN_DIR (the shadow pass): the precomputed sun clearance (sun4) seals the ray at the
+// SUN: the direction is camera.glsl's SUN_DIR (the shadow pass): the precomputed sun clearance (sun1) seals the ray at the
 // first lookup above it, and the column-tops walk is not needed.
 template <int COUNT, bool DENSE, bool SUN>
 __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool active, float ox, float oy, float oz, float dx, float dy, float dz,
@@ -564,9 +564,9 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
             if (simple && lim0 < max_steps) {  // (a run that reaches the cap seals the ray: general code)
                 limit = lim0;
                 slow = false;
-                if (SUN) {  // within < 8: the state's block is g >> 3, its column group g >> 5
+                if (SUN) {  // within < 8: the state's block is g >> 3
                     const int row = gy >> 3;
-                    if (row > (int)__ldg(&w.sun4[((uint32_t)gx >> 5) + (udim >> 2) * ((uint32_t)gz >> 5)]) && row <= w.sun_row_max) {
+                    if (row >= (int)__ldg(&w.sun1[((uint32_t)gx >> 3) + udim * ((uint32_t)gz >> 3)]) && row <= w.sun_row_max) {
                         out.trips = (uint32_t)max_steps;  // sealed: iteration-cap miss (map.glsl:167)
                         out.px = out.py = out.pz = 0xFFFFFFFFu;
                         limit = kDead;
@@ -642,10 +642,10 @@ __device__ __forceinline__ void trace_map_fast(const WorldCompact &w, bool activ
                 bool seal = COUNT != 1 && mat == 0u && limit >= max_steps;
                 limit = min(limit, max_steps);
                 if (SUN && COUNT != 1) {  // the state's sub-voxel is `pos` (within >= 0), so its block is pos >> 3
-                    const uint32_t qd = (uint32_t)w.dim >> 2;
-                    if (mat == 0u && (px >> 5) < qd && (pz >> 5) < qd) {
+                    const uint32_t qd = (uint32_t)w.dim;
+                    if (mat == 0u && (px >> 3) < qd && (pz >> 3) < qd) {
                         const int row = (int)(py >> 3);
-                        seal = seal || (row > (int)__ldg(&w.sun4[(px >> 5) + qd * (pz >> 5)]) && row <= w.sun_row_max);
+                        seal = seal || (row >= (int)__ldg(&w.sun1[(px >> 3) + qd * (pz >> 3)]) && row <= w.sun_row_max);
                     }
                 } else {
                     walk = mat == 0u && !seal && trip >= walk_at && n_free >= kWalkMinClear;

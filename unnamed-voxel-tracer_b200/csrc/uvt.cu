@@ -69,7 +69,8 @@ struct uvt_ctx {
     bool incremental_ok = false;        // the last full commit left everything uvt_world_commit_region needs
     int32_t y_clear = 0;            // max occupied block y + 1 (every block at or above is empty)
     uint16_t *d_clear4 = nullptr;   // [(dim/4)^2] dilated column-group tops for sky_sealed()
-    uint16_t *d_sun4 = nullptr;     // [(dim/4)^2] sun clearance of the shadow pass (sun_clear_kernel), built for sun_steps trips
+    uint16_t *d_sun1 = nullptr;     // [dim^2] sun clearance of the shadow pass per block column (sun_clear_kernel), built for sun_steps trips
+    uint16_t *d_top3 = nullptr;     // [dim^2] column tops grown by [-1, +2] columns: its input
     uint32_t sun_steps = 0;
     uint16_t *d_clear16 = nullptr;  // [ceil(dim/16)^2] their maxima over 16x16-block groups
     uint16_t *d_clear64 = nullptr;  // [ceil(dim/64)^2] ... over 64x64-block groups
@@ -310,7 +311,7 @@ WorldArgs<WorldCompact> world_compact(const uvt_ctx *c) {
     a.w.dim = (int32_t)c->dim;
     a.w.clear4 = c->d_clear4;
     a.w.clear16 = c->d_clear16;
-    a.w.sun4 = c->d_sun4;
+    a.w.sun1 = c->d_sun1;
     // the ray climbs at most (steps + 5) * u / (2 s + u) blocks; two blocks of slack under the top face
     a.w.sun_row_max = (int32_t)c->dim - 3 - (int32_t)std::ceil((double)(c->sun_steps + 5) * UVT_SUN_Y / (2.0 * UVT_SUN_X + UVT_SUN_Y));
     a.w.clear64 = c->d_clear64;
@@ -479,12 +480,24 @@ int launch_primary(uvt_ctx *c) {
 }
 
 // the sun clearance must cover the shadow step cap in force (it is built at commit time for the cap of that moment)
+// (re)compute the sun clearance of the block columns whose reach covers the rectangle of changed column tops
+void update_sun(uvt_ctx *c, int x0, int z0, int x1, int z1) {
+    const int dim = (int)c->dim;
+    const int tx0 = std::max(x0 - 2, 0), tz0 = std::max(z0 - 2, 0), tx1 = std::min(x1 + 1, dim - 1), tz1 = std::min(z1 + 1, dim - 1);
+    const int nt = (tx1 - tx0 + 1) * (tz1 - tz0 + 1);
+    top3_kernel<<<(nt + 255) / 256, 256, 0, c->stream>>>(c->d_tops32, c->d_top3, dim, tx0, tz0, tx1, tz1);
+    const int R = sun_reach_columns((int)c->sun_steps);
+    const int sx0 = std::max(tx0 - R, 0), sz0 = std::max(tz0 - R, 0);
+    const int ns = (tx1 - sx0 + 1) * (tz1 - sz0 + 1);
+    sun_clear_kernel<<<(ns + 255) / 256, 256, 0, c->stream>>>(c->d_top3, c->d_sun1, dim, (int)c->sun_steps, sx0, sz0, tx1, tz1);
+    c->launches += 2;
+}
+
+// the sun clearance must cover the shadow step cap in force (it is built at commit time for the cap of that moment)
 void ensure_sun(uvt_ctx *c) {
     if (!use_compact(c) || c->params.shadow_max_steps <= c->sun_steps) return;
-    const int d4 = (int)(c->dim / 4);
     c->sun_steps = c->params.shadow_max_steps;
-    sun_clear_kernel<<<(d4 * d4 + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, c->d_sun4, d4, (int)c->sun_steps);
-    c->launches++;
+    update_sun(c, 0, 0, (int)c->dim - 1, (int)c->dim - 1);
 }
 
 template <int COUNT>
@@ -530,15 +543,15 @@ int upload_material_lut(uvt_ctx *c, uint32_t *d_keys, uint8_t *d_vals) {
     return UVT_OK;
 }
 
-// clear4 from the column tops, then y_clear = its maximum
-int finish_tops(uvt_ctx *c, unsigned int *d_max) {
+// clear4 from the column tops, then y_clear = its maximum; (x0, z0)-(x1, z1) = the block columns whose tops changed
+int finish_tops(uvt_ctx *c, unsigned int *d_max, int x0, int z0, int x1, int z1) {
     const int nq = (int)((c->dim / 4) * (c->dim / 4));
     quad_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_tops32, c->d_clear4, (int)c->dim);
     const int d4 = (int)(c->dim / 4), d16 = (d4 + 3) / 4, d64 = (d16 + 3) / 4;
     coarse_clear_kernel<<<(d16 * d16 + 127) / 128, 128, 0, c->stream>>>(c->d_clear4, c->d_clear16, d4);
     coarse_clear_kernel<<<(d64 * d64 + 127) / 128, 128, 0, c->stream>>>(c->d_clear16, c->d_clear64, d16);
-    c->sun_steps = std::max<uint32_t>(c->params.shadow_max_steps, 1u);
-    sun_clear_kernel<<<(d4 * d4 + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, c->d_sun4, d4, (int)c->sun_steps);
+    c->sun_steps = std::max<uint32_t>(std::max<uint32_t>(c->params.shadow_max_steps, c->sun_steps), 1u);
+    update_sun(c, x0, z0, x1, z1);
     c->launches += 3;
     UVT_CUDA(c, cudaMemsetAsync(d_max, 0, 4, c->stream));
     max_clear_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, nq, d_max);
@@ -624,7 +637,7 @@ int build_compact(uvt_ctx *c, size_t n_bricks, size_t n_words) {
             column_tops_kernel<<<(unsigned)n_bricks, 64, 0, c->stream>>>(c->d_bricks8, c->d_brick_chunk, cd, c->d_tops32);
             c->launches++;
         }
-        int rc = finish_tops(c, d_counter);
+        int rc = finish_tops(c, d_counter, 0, 0, (int)c->dim - 1, (int)c->dim - 1);
         if (rc != UVT_OK) { cleanup(); return rc; }
     }
     {
@@ -753,7 +766,7 @@ void uvt_destroy(uvt_ctx *c) {
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
     cudaFree(c->d_chunks); cudaFree(c->d_bricks); cudaFree(c->d_bricks8); cudaFree(c->d_models); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense);
     cudaFree(c->d_rowmask); cudaFree(c->d_brick_chunk); cudaFree(c->d_tops32); cudaFree(c->d_scratch);
-    cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]); cudaFree(c->d_clear64); cudaFree(c->d_clear16); cudaFree(c->d_sun4);
+    cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]); cudaFree(c->d_clear64); cudaFree(c->d_clear16); cudaFree(c->d_sun1); cudaFree(c->d_top3);
     cudaFree(c->d_mat_word); cudaFree(c->d_mat_color); cudaFree(c->d_mat_mask);
     cudaFree(c->d_cams); cudaFree(c->d_counters); cudaFree(c->d_pick); cudaFree(c->d_sink); cudaFree(c->shared_frame); cudaFree(c->d_ent_model);
     for (int i = 0; i < 4; ++i)
@@ -851,8 +864,8 @@ int uvt_pipeline_dispatch(uvt_pipeline *p, uint32_t gx, uint32_t gy, uint32_t gz
 static int reset_world(uvt_ctx *c, uint32_t dim) {
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!c->staging_borrowed) { cudaFreeHost(c->h_chunks); cudaFreeHost(c->h_bricks); }
-    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32); cudaFree(c->d_clear64); cudaFree(c->d_clear16); cudaFree(c->d_sun4);
-    c->d_clear64 = c->d_clear16 = c->d_sun4 = nullptr;
+    cudaFree(c->d_chunks); cudaFree(c->d_chunks2); cudaFree(c->d_clear4); cudaFree(c->d_dense); cudaFree(c->d_tops32); cudaFree(c->d_clear64); cudaFree(c->d_clear16); cudaFree(c->d_sun1); cudaFree(c->d_top3);
+    c->d_clear64 = c->d_clear16 = c->d_sun1 = c->d_top3 = nullptr;
     cudaFree(c->d_field); cudaFree(c->d_field_tmp[0]); cudaFree(c->d_field_tmp[1]);
     c->d_field = c->d_field_tmp[0] = c->d_field_tmp[1] = nullptr;
     c->d_dense = nullptr;
@@ -875,7 +888,8 @@ static int reset_world(uvt_ctx *c, uint32_t dim) {
     UVT_CUDA(c, cudaMalloc(&c->d_chunks2, (size_t)(c->cd + 1) * (c->cd + 1) * (c->cd + 1) * 4));
     UVT_CUDA(c, cudaMalloc(&c->d_clear4, (size_t)(dim / 4) * (dim / 4) * 2));
     UVT_CUDA(c, cudaMalloc(&c->d_clear16, (size_t)((dim + 15) / 16) * ((dim + 15) / 16) * 2));
-    UVT_CUDA(c, cudaMalloc(&c->d_sun4, (size_t)(dim / 4) * (dim / 4) * 2));
+    UVT_CUDA(c, cudaMalloc(&c->d_sun1, (size_t)dim * dim * 2));
+    UVT_CUDA(c, cudaMalloc(&c->d_top3, (size_t)dim * dim * 2));
     UVT_CUDA(c, cudaMalloc(&c->d_clear64, (size_t)((dim + 63) / 64) * ((dim + 63) / 64) * 2));
     return UVT_OK;
 }
@@ -1145,7 +1159,7 @@ static int commit_region_impl(uvt_ctx *c, size_t n_bricks, const uint32_t lo[3],
                                   (size_t)bz * 8, c->stream));
     column_tops_box_kernel<<<dim3((unsigned)bx, (unsigned)cd, (unsigned)bz), 64, 0, c->stream>>>(c->d_chunks, c->d_bricks8, cd, o[0], o[2], c->d_tops32);
     c->launches++;
-    rc = finish_tops(c, d_flags + 4);
+    rc = finish_tops(c, d_flags + 4, o[0] * 8, o[2] * 8, (o[0] + bx) * 8 - 1, (o[2] + bz) * 8 - 1);
     if (rc != UVT_OK) return rc;
 
     // ---- clearances and dense bytes of the box grown by two chunks
@@ -1208,8 +1222,11 @@ int uvt_world_layout_checksum(uvt_ctx *c, uint64_t out[4]) {
     const int cd = (int)c->cd;
     const int nq = (int)((c->dim / 4) * (c->dim / 4));
     layout_checksum_kernel<<<(unsigned)((size_t)cd * cd * cd), 64, 0, c->stream>>>(c->d_chunks2, c->d_bricks8, c->dense_valid ? c->d_dense : nullptr, c->d_mat_word, cd, d);
-    clear4_checksum_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, nq, d);
-    c->launches += 2;
+    clear4_checksum_kernel<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_clear4, nq, d, 7ull);
+    const int n1 = (int)(c->dim * c->dim);  // the sun clearance and its input follow the column tops as well
+    clear4_checksum_kernel<<<(n1 + 255) / 256, 256, 0, c->stream>>>(c->d_top3, n1, d, 0xA3ull << 32);
+    clear4_checksum_kernel<<<(n1 + 255) / 256, 256, 0, c->stream>>>(c->d_sun1, n1, d, 0x51ull << 32);
+    c->launches += 4;
     unsigned long long h[4] = {0, 0, 0, 0};
     cudaError_t e = cudaMemcpyAsync(h, d, 32, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
