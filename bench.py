@@ -68,6 +68,7 @@ def parse_args():
                     help="tiled frames: p2p = kernels store finished bands straight into rank 0's frame over NVLink (CUDA IPC peer mapping); "
                          "nccl = uvt_dispatch_frame_nccl: grouped ncclSend/ncclRecv per band group on a second stream, overlapped with the traversal of the next group")
     ap.add_argument("--band-rows", type=int, default=16, help="rows per band of a tiled frame (a multiple of 16); 16 keeps the ranks' row counts within 1 %% of each other at 4K / 8 ranks")
+    ap.add_argument("--frame-chunks", type=int, default=0, help="uvt_set_frame_chunks for the timed frames (0 = 2 for tiled p2p frames, 1 otherwise)")
     ap.add_argument("--nccl-groups", type=int, default=4, help="band groups per rank of the NCCL exchange (1 = exchange after the whole frame)")
     return ap.parse_args()
 
@@ -400,6 +401,11 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
             ctx.nccl_init(D.bcast(uvt.Context.nccl_unique_id() if rank == 0 else None), world, rank)
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=D.dev)
 
+    # tiled frames: the rank's rows in two chunks on two streams, so that the tail of one chunk's pass runs under the other's work
+    # (uvt_set_frame_chunks; -12 % at 1/8 of a 4K frame per GPU).  N = 1 keeps whole-frame launches: every pass has its own time.
+    chunks = args.frame_chunks if args.frame_chunks else (2 if (tiled and p2p) else 1)
+    ctx.set_frame_chunks(chunks)
+
     def device_step(i):
         """One pass of the hot path, inputs resident.  Device ms from CUDA events on the launch stream."""
         if sweep:
@@ -410,7 +416,7 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
             return ctx.last_pass_ms("frame"), None
         if shadows:
             ctx.dispatch_frame()
-            return ctx.last_pass_ms("frame"), ctx.last_pass_ms("primary")
+            return ctx.last_pass_ms("frame"), (None if chunks > 1 else ctx.last_pass_ms("primary"))
         ctx.dispatch_primary()
         ms = ctx.last_pass_ms("primary")
         return ms, ms
@@ -460,9 +466,20 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
     clocks = sampler.stop()
 
     pass_ms = None
-    if shadows:  # per-pass device time, averaged over the timed steps is not kept per pass: take one more frame
+    chunked_ms = None
+    if shadows:  # per-pass device time, averaged over the timed steps is not kept per pass: take one more (whole-frame) frame
+        ctx.set_frame_chunks(1)
         ctx.dispatch_frame(); ctx.sync()
         pass_ms = {k: ctx.last_pass_ms(k) for k in ("primary", "secondary", "shade")}
+        if chunks == 1 and not (tiled and not p2p):  # what uvt_set_frame_chunks(2) would give (outside the timed region, L2 warm on both sides)
+            t1, t2 = [], []
+            for n_, acc in ((1, t1), (2, t2)):
+                ctx.set_frame_chunks(n_)
+                for _ in range(12):
+                    ctx.dispatch_frame(); ctx.sync()
+                    acc.append(ctx.last_pass_ms("frame"))
+            chunked_ms = {"whole_frame_launches": float(np.median(t1[2:])), "two_row_chunks_on_two_streams": float(np.median(t2[2:]))}
+        ctx.set_frame_chunks(chunks)
 
     verified = None
     if tiled:
@@ -575,6 +592,9 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
         }
         if pass_ms:
             rec["pass_ms"] = pass_ms
+        rec["config"]["frame_chunks"] = chunks
+        if chunked_ms:
+            rec["frame_chunks_ms"] = chunked_ms
         if tiled:
             rec["config"]["exchange"] = ("p2p: every rank's shade kernel stores its finished bands into rank 0's frame over NVLink (CUDA IPC peer mapping), inside the timed region"
                                          if p2p else "nccl: uvt_dispatch_frame_nccl, %d band groups per rank; each group's bands go to their rows of rank 0's frame by grouped "

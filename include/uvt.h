@@ -222,6 +222,11 @@ int  uvt_set_entities(uvt_ctx *ctx, const float *positions_xyz, uint32_t n);
  * max_steps = the cap of the model loop (map.glsl:214), 0 = 64. */
 int  uvt_entity_model_upload(uvt_ctx *ctx, uint32_t size, const uint32_t *rgba, uint32_t max_steps);
 
+/* uvt_dispatch_frame in n row chunks (1 = whole-frame launches, the default): chunk k runs its three passes on the ctx
+ * stream, chunk k+1 on a side stream, so the tail of one pass (a few long-running warps) overlaps the next chunk's work.
+ * Worth it when a GPU's share of the frame is small (tiled frames at N = 4, 8); identical pixels.  With n > 1 only
+ * the frame has a time (uvt_last_pass_ms 3). */
+int  uvt_set_frame_chunks(uvt_ctx *ctx, uint32_t n);
 /* terrain_edit.comp.glsl: the centre pick ray, traceMap(...,64); returns the hit. */
 int  uvt_pick(uvt_ctx *ctx, uvt_hit *out);
 int  uvt_sync(uvt_ctx *ctx);

@@ -1347,3 +1347,37 @@ def test_sun_clearance_against_adversarial_terrain_and_step_caps(uvt, oracle, sc
         sc.bm.mark_dirty()
         sc.bm.bind(9)   # full commit of the same world
         assert ctx.world_layout_checksum() == inc
+
+
+def test_frame_in_row_chunks_equals_whole_frame_launches(uvt, oracle, w1):
+    """uvt_set_frame_chunks: the same kernels over row chunks on two streams — every G-buffer image, the hit buffer and the
+    frame are the whole-frame launches' bit for bit (also under a band partition and with the entity passes on)."""
+    ctx, sc = w1
+    ctx.set_layout("compact")
+    cam = camera_k1(uvt, oracle)
+    try:
+        for part in (None, (16, 4, 1)):
+            if part:
+                ctx.set_partition(*part)
+            ctx.resize(640, 360)
+            ctx.set_frame_chunks(1)
+            a = gpu_render(ctx, cam, three_pass=False)
+            for n in (2, 3, 8):
+                ctx.set_frame_chunks(n)
+                b = gpu_render(ctx, cam, three_pass=False)
+                for k in ("albedo", "normal", "illumination", "frame"):
+                    assert np.array_equal(a[k], b[k]), (part, n, k)
+                assert np.array_equal(a["position"].view(np.uint32), b["position"].view(np.uint32))
+                assert np.array_equal(a["hits"], b["hits"])
+        ctx.set_partition(8, 1, 0)
+        ctx.resize(320, 180)
+        ctx.set_entity_mode("models")
+        p, pitch, yaw = ENTITY_CAMERAS[0]
+        ecam = oracle.make_camera(p, pitch_yaw_matrix(uvt, pitch, yaw))
+        ctx.set_frame_chunks(2)
+        r = oracle.render(sc.oracle_world, ecam, 320, 180, oracle.params(512, ent=oracle.entities("models")))
+        assert_frame_parity(gpu_render(ctx, ecam, three_pass=False), r)
+    finally:
+        ctx.set_frame_chunks(1)
+        ctx.set_entity_mode("boxes")
+        ctx.set_partition(8, 1, 0)

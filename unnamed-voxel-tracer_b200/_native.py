@@ -85,6 +85,7 @@ SIGNATURES = {
     "uvt_set_entity_mode": (c_int, [c_p, c_u32]),
     "uvt_set_entities": (c_int, [c_p, c_p, c_u32]),
     "uvt_entity_model_upload": (c_int, [c_p, c_u32, c_p, c_u32]),
+    "uvt_set_frame_chunks": (c_int, [c_p, c_u32]),
     "uvt_pick": (c_int, [c_p, c_p]),
     "uvt_sync": (c_int, [c_p]),
     "uvt_readback": (c_int, [c_p, c_int, c_p, c_size]),

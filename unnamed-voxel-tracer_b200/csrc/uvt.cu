@@ -138,6 +138,11 @@ struct uvt_ctx {
         bool planned = false;
     } pgen;
 
+    // ---- frame in row chunks on two streams (uvt_set_frame_chunks): the tail of one chunk's pass runs under the next chunk's work
+    uint32_t frame_chunks = 1;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+
     // ---- entities (uvt_set_entity_mode / uvt_set_entities / uvt_entity_model_upload)
     uint32_t ent_mode = UVT_ENTITY_BOXES;
     std::vector<float> ent_pos;          // xyz per entity; empty: the five literal positions of map.glsl:173-179
@@ -401,6 +406,8 @@ int check_launch(uvt_ctx *c, const char *what) {
     c->launches++;
     return UVT_OK;
 }
+
+int launch_rows(uvt_ctx *c, uint32_t row0, uint32_t nrows);  // the three passes over a row range (defined with the band exchange)
 
 int pre_dispatch(uvt_ctx *c) {
     UVT_REQUIRE(c, c->W && c->H, "no G-buffer (uvt_resize first)");
@@ -772,6 +779,9 @@ void uvt_destroy(uvt_ctx *c) {
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 2; ++j)
             if (c->ev[i][j]) cudaEventDestroy(c->ev[i][j]);
+    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+    if (c->join_ev) cudaEventDestroy(c->join_ev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -1364,6 +1374,32 @@ int uvt_dispatch_frame(uvt_ctx *c) {
     const dim3 grid = trace_grid(c);
     const CamDev *cams = c->layers > 1 ? c->d_cams : nullptr;
     PassTimer t(c, 3);
+    const uint32_t all_rows = storage_rows(c->H, c->band_rows, c->n_parts, c->part);
+    if (c->frame_chunks > 1 && c->layers == 1 && !use_pool(c) && all_rows >= 32u * c->frame_chunks) {
+        // Row chunks alternate between the ctx stream and a side stream: chunk k+1's primary pass fills the SMs that the tail of
+        // chunk k's pass leaves idle (a pass ends with a few long-running warps; at 1/8 of a 4K frame per GPU that tail is a
+        // quarter of the pass).  Same kernels, same pixels: results are identical to the whole-frame launches.
+        ensure_sun(c);
+        if (!c->side_stream) {
+            UVT_CUDA(c, cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+            UVT_CUDA(c, cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+            UVT_CUDA(c, cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
+        }
+        c->ev_valid[0] = c->ev_valid[1] = c->ev_valid[2] = false;  // the passes of different chunks overlap: only the frame has a time
+        UVT_CUDA(c, cudaEventRecord(c->fork_ev, c->stream));
+        UVT_CUDA(c, cudaStreamWaitEvent(c->side_stream, c->fork_ev, 0));
+        cudaStream_t main_stream = c->stream;
+        const uint32_t per = ((all_rows + c->frame_chunks - 1) / c->frame_chunks + 15u) & ~15u;  // multiples of the CTA tile height
+        for (uint32_t k = 0, r0 = 0; r0 < all_rows && rc == UVT_OK; ++k, r0 += per) {
+            c->stream = (k & 1u) ? c->side_stream : main_stream;
+            rc = launch_rows(c, r0, std::min(per, all_rows - r0));
+        }
+        c->stream = main_stream;
+        if (rc != UVT_OK) return rc;
+        UVT_CUDA(c, cudaEventRecord(c->join_ev, c->side_stream));
+        UVT_CUDA(c, cudaStreamWaitEvent(c->stream, c->join_ev, 0));
+        return UVT_OK;
+    }
     if (use_pool(c) || !(c->params.flags & UVT_FLAG_FUSED_FRAME) || ent_custom(c)) {
         // the three passes of game.zig:244-255 as three launches: measured faster than the fused kernel (c1 0.301 vs
         // 0.324 ms, c3 2.21 vs 2.41 ms) — the G-buffer round trip through L2 costs less than the registers and the
@@ -1442,6 +1478,14 @@ int uvt_entity_model_upload(uvt_ctx *c, uint32_t size, const uint32_t *rgba, uin
     UVT_CUDA(c, cudaMalloc(&c->d_ent_model, bytes));
     UVT_CUDA(c, cudaMemcpy(c->d_ent_model, rgba, bytes, cudaMemcpyHostToDevice));
     c->ent_size = size;
+    return UVT_OK;
+}
+
+int uvt_set_frame_chunks(uvt_ctx *c, uint32_t n) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    UVT_REQUIRE(c, n >= 1 && n <= 8, "1..8 row chunks");
+    c->frame_chunks = n;
     return UVT_OK;
 }
 

@@ -157,6 +157,10 @@ class Context:
     def sync(self):
         self.check(self.L.uvt_sync(self.handle))
 
+    def set_frame_chunks(self, n):
+        """dispatch_frame in n row chunks alternating between two streams (hides pass tails when the frame share is small)."""
+        self.check(self.L.uvt_set_frame_chunks(self.handle, int(n)))
+
     def set_entity_mode(self, mode):
         """traceEntities (map.glsl:172-248): "boxes" = the reference as it runs (returns at :199), "models" = the sub-model
         DDA behind that return + the primary-pass composite of primary.comp.glsl:45-54 (turns the hit buffer on)."""
