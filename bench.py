@@ -67,7 +67,8 @@ def parse_args():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="tiled frames: p2p = kernels store finished bands straight into rank 0's frame over NVLink (CUDA IPC peer mapping); "
                          "nccl = uvt_dispatch_frame_nccl: grouped ncclSend/ncclRecv per band group on a second stream, overlapped with the traversal of the next group")
-    ap.add_argument("--band-rows", type=int, default=16, help="rows per band of a tiled frame (a multiple of 16); 16 keeps the ranks' row counts within 1 %% of each other at 4K / 8 ranks")
+    ap.add_argument("--band-rows", type=int, default=0, help="rows per band of a tiled frame (a multiple of 16); default 16 for the p2p band stores (keeps the ranks' row counts "
+                    "within 1 %% of each other at 4K / 8 ranks), 32 for the NCCL exchange (half as many send/recv pairs)")
     ap.add_argument("--frame-chunks", type=int, default=0, help="uvt_set_frame_chunks for the timed frames (0 = 2 for tiled p2p frames, 1 otherwise)")
     ap.add_argument("--nccl-groups", type=int, default=4, help="band groups per rank of the NCCL exchange (1 = exchange after the whole frame)")
     return ap.parse_args()
@@ -359,7 +360,7 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
     dim, W, H, shadows, desc = WORKLOADS[workload]
     sweep = workload == "c5"
     tiled = world > 1 and workload in ("c1", "c3", "c4")   # one frame cut into bands across the ranks (strong scaling)
-    band = args.band_rows
+    band = args.band_rows or (16 if args.gather == "p2p" else 32)
 
     ctx = uvt.Context(local_rank, map_dim=dim, layout=args.layout, dense=not args.no_dense, fused_frame=args.fused_frame)
     ctx.set_scheduler(args.scheduler)
