@@ -365,26 +365,44 @@ __global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) secondary_kernel(Wor
     }
 }
 
-// blit.fragment.glsl:23-36 for one pixel
+// SkyDome2 once more, for the blit only: the shaded frame is held to the reference within 1/255 per channel, which
+// leaves room for a reciprocal square root and plain multiplications (relative error ~1e-6) where the primary pass's sky colour
+// keeps the exactly rounded divisions.
+__device__ __forceinline__ void sky_dome2_fast(float rx, float ry, float rz, float &r, float &g, float &b) {
+    const float inv_sl = 0.7991607f;  // 1 / |SUN_DIR|
+    const float inv_rl = rsqrtf(rx * rx + ry * ry + rz * rz);
+    const float dot = (UVT_SUN_X * rx + UVT_SUN_Y * ry + UVT_SUN_Z * rz) * (inv_sl * inv_rl);
+    const float sun = fminf(fmaxf(dot, 0.0f), 1.2f);
+    const float s2 = sun * sun, s4 = s2 * s2, p8 = s4 * s4, p3 = s2 * sun;
+    const float k = ry * 0.2f;
+    r = 0.675f - k + 0.4f * p8 + 0.2f * p3;
+    g = 0.785f - k * 0.5f + 0.24f * p8 + 0.08f * p3;
+    b = 0.825f - k + 0.04f * p8 + 0.04f * p3;
+}
+
+// blit.fragment.glsl:23-36 for one pixel.  Within the 1/255 tolerance of the frame: texel bytes become floats by a multiplication,
+// the vignette's pow runs through exp2 / log2 (__powf), the lit term uses sky_dome2_fast and is skipped where it is multiplied by an
+// illumination alpha of 0 (shadowed pixels: `color += 0 * SkyDome2(..)`).  The crosshair predicate stays exact — a pixel flipping
+// in or out of it would change by half its value.
 __device__ __forceinline__ uint32_t shade_pixel(const ViewDev &v, uint32_t x, uint32_t y, uint32_t albedo, uint32_t illum) {
     const float tx = ((float)x + 0.5f) / (float)v.W, ty = ((float)y + 0.5f) / (float)v.H;
+    const float k255 = 1.0f / 255.0f;
     float c[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) c[k] = (float)((albedo >> (8 * k)) & 255u) / 255.0f;
-    if (illum != 0u) {
-        const float ir = (float)(illum & 255u) / 255.0f, ig = (float)((illum >> 8) & 255u) / 255.0f,
-                    ib = (float)((illum >> 16) & 255u) / 255.0f, ia = (float)(illum >> 24) / 255.0f;
+    for (int k = 0; k < 4; ++k) c[k] = (float)((albedo >> (8 * k)) & 255u) * k255;
+    if ((illum >> 24) != 0u) {
+        const float ia = (float)(illum >> 24) * k255;
         float r, g, b;
-        sky_dome2(ir, ig, ib, r, g, b);
-        c[0] = c[0] + ia * r; c[1] = c[1] + ia * g; c[2] = c[2] + ia * b; c[3] = c[3] + ia * 1.0f;
+        sky_dome2_fast((float)(illum & 255u) * k255, (float)((illum >> 8) & 255u) * k255, (float)((illum >> 16) & 255u) * k255, r, g, b);
+        c[0] += ia * r; c[1] += ia * g; c[2] += ia * b; c[3] += ia;
     }
     const float cx = tx - 0.5f, cy = ty - 0.5f;
-    if (sqrtf(cx * cx + cy * cy) <= 0.002f) {
-        c[0] = c[0] * 0.5f + 1.0f * 0.5f; c[1] = c[1] * 0.5f + 1.0f * 0.5f;
-        c[2] = c[2] * 0.5f + 1.0f * 0.5f; c[3] = c[3] * 0.5f + 0.4f * 0.5f;
+    if (fabsf(cx) <= 0.0021f && fabsf(cy) <= 0.0021f && sqrtf(cx * cx + cy * cy) <= 0.002f) {  // :33 mix(color, (1,1,1,0.4), 0.5)
+        c[0] = c[0] * 0.5f + 0.5f; c[1] = c[1] * 0.5f + 0.5f;
+        c[2] = c[2] * 0.5f + 0.5f; c[3] = c[3] * 0.5f + 0.2f;
     }
     const float vx = tx * (1.0f - tx), vy = ty * (1.0f - ty);
-    const float grad = powf(vx * vy * 15.0f, 0.6f * 0.3f);
+    const float grad = __powf(vx * vy * 15.0f, 0.6f * 0.3f);
     return pack_rgba8(grad * c[0], grad * c[1], grad * c[2], grad * c[3]);
 }
 
