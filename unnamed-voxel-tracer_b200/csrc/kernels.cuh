@@ -730,32 +730,34 @@ __global__ void coarse_clear_kernel(const uint16_t *__restrict__ in, uint16_t *_
 // block row r.  Travelling up every axis the state never moves down or back: `within += dir * t` adds non-negative numbers and
 // a reset puts the stepped axis exactly on the face it reached, so in fp32, too, every later state has y >= the row's floor.
 // A lookup names the state's block or, when a `within` component has rounded up to the step size, the next one up that axis —
-// never a lower row, at most one column further.  The line runs along the diagonal of the x-z plane (s_x = s_z): it can only
-// visit columns (X + a, Z + b) with a, b >= 0 and |a - b| <= 1, and it is inside such a column only after an x- (or z-)
-// advance of more than max(a, b) - 1 blocks, i.e. after climbing (u / s) * max(max(a, b) - 1, 0) blocks (the real trajectory
-// follows the ideal line to ~1e-5 block over 48 trips; 0.01 block of the credit is given up for that).  Hence with
-//     top3[c]  = the highest column top (first all-empty row) over columns c + [-1, +2]^2   (carry + one column of drift)
-//     sun1[X,Z] = max over the reachable (a, b) of  ceil(top3[X + a, Z + b] - max((u / s) * max(max(a, b) - 1, 0) - 0.01, 0))
+// never a lower row, at most one column further in +x and / or +z: top2[c] = the highest column top (first all-empty row) over
+// columns c + [0, 1]^2 covers every lookup made from column c.  The line runs along the diagonal of the x-z plane
+// (s_x = s_z): it only visits columns (X + a, Z + b) with a, b >= 0 and |a - b| <= 1, and it is inside such a column only after
+// an x- (or z-) advance of more than max(a, b) - 1 blocks, i.e. after climbing (u / s) * max(max(a, b) - 1, 0) blocks.  The
+// real trajectory follows the ideal line to ~1e-5 block over 48 trips: 0.01 block of every credit is given up for that, and the
+// columns (X + k + 1, Z + k - 1), (X + k - 1, Z + k + 1) a drifting state could clip at a cell corner are scanned too (with the
+// credit of one step less).  Hence with
+//     sun1[X,Z] = max over the scanned (a, b) of  ceil(top2[X + a, Z + b] - max(credit(a, b) - 0.01, 0))
 // a state in a row >= sun1 looks up nothing but empty blocks for `steps` trips.  Columns beyond the x / z faces make the
 // value infinite (the ray could leave the map before the cap); the top face is the caller's sun_row_max.  Reach: `steps`
 // trips cover at most (steps + 5) / (2 s + u) of parameter, s times that along x.
 // (x0, z0)-(x1, z1): the rectangle of columns to (re)compute, inclusive — everything, or the surroundings of an edit.
-__global__ void top3_kernel(const unsigned int *__restrict__ tops32, uint16_t *__restrict__ top3, int dim, int x0, int z0, int x1, int z1) {
+__global__ void top3_kernel(const unsigned int *__restrict__ tops32, uint16_t *__restrict__ top2, int dim, int x0, int z0, int x1, int z1) {
     const int w = x1 - x0 + 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w * (z1 - z0 + 1)) return;
     const int x = x0 + i % w, z = z0 + i / w;
     unsigned int m = 0;
-    for (int zz = max(z - 1, 0); zz <= min(z + 2, dim - 1); ++zz)
-        for (int xx = max(x - 1, 0); xx <= min(x + 2, dim - 1); ++xx) m = max(m, tops32[(size_t)xx + (size_t)dim * zz]);
-    top3[(size_t)x + (size_t)dim * z] = (uint16_t)min(m, 0xFFFEu);
+    for (int zz = z; zz <= min(z + 1, dim - 1); ++zz)
+        for (int xx = x; xx <= min(x + 1, dim - 1); ++xx) m = max(m, tops32[(size_t)xx + (size_t)dim * zz]);
+    top2[(size_t)x + (size_t)dim * z] = (uint16_t)min(m, 0xFFFEu);
 }
 
 __host__ __device__ inline int sun_reach_columns(int steps) {
     return (int)(UVT_SUN_X * (float)(steps + 5) / (2.0f * UVT_SUN_X + UVT_SUN_Y)) + 2;
 }
 
-__global__ void sun_clear_kernel(const uint16_t *__restrict__ top3, uint16_t *__restrict__ sun1, int dim, int steps, int x0, int z0, int x1, int z1) {
+__global__ void sun_clear_kernel(const uint16_t *__restrict__ top2, uint16_t *__restrict__ sun1, int dim, int steps, int x0, int z0, int x1, int z1) {
     const int w = x1 - x0 + 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w * (z1 - z0 + 1)) return;
@@ -765,13 +767,14 @@ __global__ void sun_clear_kernel(const uint16_t *__restrict__ top3, uint16_t *__
     int m = 0;
     bool open = false;
     for (int k = 0; k <= K; ++k) {
-        const float credit = fmaxf(climb * (float)max(k - 1, 0) - 0.01f, 0.0f);
-        for (int j = 0; j < 3; ++j) {  // (a, b) = (k, k), (k, k - 1), (k - 1, k)
-            const int a = j == 2 ? k - 1 : k, b = j == 1 ? k - 1 : k;
+        const float credit = fmaxf(climb * (float)max(k - 1, 0) - 0.01f, 0.0f), credit_drift = fmaxf(climb * (float)max(k - 2, 0) - 0.01f, 0.0f);
+        for (int j = 0; j < 5; ++j) {  // (a, b) = (k, k), (k, k - 1), (k - 1, k); corner drift: (k + 1, k - 1), (k - 1, k + 1)
+            const int a = j == 2 ? k - 1 : (j == 3 ? k + 1 : (j == 4 ? k - 1 : k));
+            const int b = j == 1 ? k - 1 : (j == 3 ? k - 1 : (j == 4 ? k + 1 : k));
             if (a < 0 || b < 0) continue;
             const int cx = x + a, cz = z + b;
             if (cx >= dim || cz >= dim) { open = true; continue; }
-            m = max(m, (int)ceilf((float)top3[(size_t)cx + (size_t)dim * cz] - credit));
+            m = max(m, (int)ceilf((float)top2[(size_t)cx + (size_t)dim * cz] - (j >= 3 ? credit_drift : credit)));
         }
     }
     sun1[(size_t)x + (size_t)dim * z] = open ? (uint16_t)0xFFFF : (uint16_t)min(m, 0xFFFE);

@@ -70,7 +70,7 @@ struct uvt_ctx {
     int32_t y_clear = 0;            // max occupied block y + 1 (every block at or above is empty)
     uint16_t *d_clear4 = nullptr;   // [(dim/4)^2] dilated column-group tops for sky_sealed()
     uint16_t *d_sun1 = nullptr;     // [dim^2] sun clearance of the shadow pass per block column (sun_clear_kernel), built for sun_steps trips
-    uint16_t *d_top3 = nullptr;     // [dim^2] column tops grown by [-1, +2] columns: its input
+    uint16_t *d_top3 = nullptr;     // [dim^2] column tops grown by [0, +1] columns (top2 of sun_clear_kernel): its input
     uint32_t sun_steps = 0;
     uint16_t *d_clear16 = nullptr;  // [ceil(dim/16)^2] their maxima over 16x16-block groups
     uint16_t *d_clear64 = nullptr;  // [ceil(dim/64)^2] ... over 64x64-block groups
@@ -486,14 +486,14 @@ int launch_primary(uvt_ctx *c) {
     return launch_entity_primary(c, v, g, storage_rows(c->H, c->band_rows, c->n_parts, c->part), c->layers);
 }
 
-// the sun clearance must cover the shadow step cap in force (it is built at commit time for the cap of that moment)
 // (re)compute the sun clearance of the block columns whose reach covers the rectangle of changed column tops
 void update_sun(uvt_ctx *c, int x0, int z0, int x1, int z1) {
     const int dim = (int)c->dim;
-    const int tx0 = std::max(x0 - 2, 0), tz0 = std::max(z0 - 2, 0), tx1 = std::min(x1 + 1, dim - 1), tz1 = std::min(z1 + 1, dim - 1);
+    // top2[c] reads the tops of columns c + [0, 1]^2; sun1[X] reads top2 of X + [0, R + 1]
+    const int tx0 = std::max(x0 - 1, 0), tz0 = std::max(z0 - 1, 0), tx1 = std::min(x1, dim - 1), tz1 = std::min(z1, dim - 1);
     const int nt = (tx1 - tx0 + 1) * (tz1 - tz0 + 1);
     top3_kernel<<<(nt + 255) / 256, 256, 0, c->stream>>>(c->d_tops32, c->d_top3, dim, tx0, tz0, tx1, tz1);
-    const int R = sun_reach_columns((int)c->sun_steps);
+    const int R = sun_reach_columns((int)c->sun_steps) + 1;
     const int sx0 = std::max(tx0 - R, 0), sz0 = std::max(tz0 - R, 0);
     const int ns = (tx1 - sx0 + 1) * (tz1 - sz0 + 1);
     sun_clear_kernel<<<(ns + 255) / 256, 256, 0, c->stream>>>(c->d_top3, c->d_sun1, dim, (int)c->sun_steps, sx0, sz0, tx1, tz1);
