@@ -106,8 +106,20 @@ pub const VoxelModelAtlas = struct {
     pub fn bind(_: *@This(), _: u32) void {}
 };
 
-/// procgen.zig's entry point, running in the native library on the brickmap's pinned staging.
+/// procgen.zig's entry point.  A fresh map bound to a ctx is generated on the GPU (same LCG stream, byte-identical world:
+/// uvt_procgen_device); anything the device path does not cover falls back to the serial host version on the pinned staging.
 pub fn procgen(comptime dim: comptime_int, world: anytype, offsetX: f32, offsetY: f32) void {
-    _ = c.uvt_procgen(world.handle, dim, offsetX, offsetY);
+    if (c.uvt_procgen_device(world.handle, dim, offsetX, offsetY) != c.UVT_OK)
+        _ = c.uvt_procgen(world.handle, dim, offsetX, offsetY);
     world.dirty = true;
+}
+
+/// traceEntities (map.glsl:172-248).  Nothing to call for the reference as it runs (five literal boxes, shadow pass only).
+/// `enableEntityModels` switches on what the reference keeps dead / commented: the sub-model DDA and the primary-pass
+/// composite, with the entity model the commented `models.load_model("assets/chicken.vox", allocator, 32)` of game.zig:114
+/// would have loaded (texels: size^3 RGBA8, x fastest, then y, then z).
+pub fn enableEntityModels(positions: []const [3]f32, texels: ?[]const u32, size: u32) void {
+    uvt.check(c.uvt_set_entities(uvt.ctx, @ptrCast(positions.ptr), @intCast(positions.len))) catch {};
+    if (texels) |t| uvt.check(c.uvt_entity_model_upload(uvt.ctx, size, t.ptr, 8 * size)) catch {};
+    uvt.check(c.uvt_set_entity_mode(uvt.ctx, c.UVT_ENTITY_MODELS)) catch {};
 }
