@@ -207,7 +207,13 @@ __device__ __forceinline__ void warp_add(unsigned long long *dst, uint32_t v) {
 #define UVT_MIN_BLOCKS_FRAME 7  // the fused frame kernel keeps two rays' worth of state: <= 73 registers measured faster than <= 51
 #endif
 constexpr int kWarpW = UVT_WARP_W, kWarpH = 32 / UVT_WARP_W;
-constexpr int kTileW = 2 * kWarpW, kTileH = 2 * kWarpH, kThreads = 128;
+#ifndef UVT_CTA_WARPS
+#define UVT_CTA_WARPS 4  // warps per CTA of the pixel-per-thread kernels, two abreast (experiment knob: 2 = 64-thread CTAs)
+#endif
+constexpr int kThreads = 128;                     // pooled-scheduler kernels
+constexpr int kTileThreads = 32 * UVT_CTA_WARPS;  // pixel-per-thread kernels
+constexpr int kTileW = 2 * kWarpW, kTileH = (UVT_CTA_WARPS / 2) * kWarpH;
+static_assert(UVT_CTA_WARPS == 2 || UVT_CTA_WARPS == 4 || UVT_CTA_WARPS == 8, "warps are laid out two abreast");
 static_assert(kWarpW * kWarpH == 32, "a warp covers 32 pixels");
 
 __device__ __forceinline__ void tile_pixel(uint32_t &x, uint32_t &ly) {
@@ -250,7 +256,7 @@ struct WorldArgs<WorldDense> {
 
 // ---- primary pass ------------------------------------------------------------------------
 template <class World, int COUNT, bool HITBUF, bool BATCH>
-__global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) primary_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0,
+__global__ void __launch_bounds__(kTileThreads, UVT_MIN_BLOCKS) primary_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0,
                                                            ViewDev v, GBufDev gb, DevCounters *counters) {
     __shared__ uint32_t s_masks[(UVT_SMEM_MASKS && kIsCompact<World>) ? kSmemMaskMats * 16 : 1];
     World w = wa.w;
@@ -328,7 +334,7 @@ __device__ __forceinline__ uint32_t shadow_pixel(const World &w, bool active, co
 
 // ---- secondary pass ------------------------------------------------------------------------
 template <class World, int COUNT>
-__global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS) secondary_kernel(WorldArgs<World> wa, ViewDev v, GBufDev gb, DevCounters *counters) {
+__global__ void __launch_bounds__(kTileThreads, UVT_MIN_BLOCKS) secondary_kernel(WorldArgs<World> wa, ViewDev v, GBufDev gb, DevCounters *counters) {
     __shared__ uint32_t s_masks[(UVT_SMEM_MASKS && kIsCompact<World>) ? kSmemMaskMats * 16 : 1];
     World w = wa.w;
     if constexpr (kIsCompact<World>) {
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(256) shade_kernel(ViewDev v, GBufDev gb, Frame
 // Results are identical to the three separate passes: the shadow ray starts from the same
 // quantised position/normal the G-buffer would hold.
 template <class World, bool GBUF, bool BATCH>
-__global__ void __launch_bounds__(kThreads, UVT_MIN_BLOCKS_FRAME) frame_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0, ViewDev v,
+__global__ void __launch_bounds__(kTileThreads, UVT_MIN_BLOCKS_FRAME) frame_kernel(WorldArgs<World> wa, const CamDev *__restrict__ cams, CamDev cam0, ViewDev v,
                                                          uint32_t shadow_steps, GBufDev gb, FrameTarget ft) {
     __shared__ uint32_t s_masks[(UVT_SMEM_MASKS && kIsCompact<World>) ? kSmemMaskMats * 16 : 1];
     World w = wa.w;

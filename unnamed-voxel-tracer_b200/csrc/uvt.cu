@@ -419,7 +419,7 @@ template <class World, int COUNT>
 void launch_primary_world(uvt_ctx *c, const WorldArgs<World> &wa, const ViewDev &v, const GBufDev &g, dim3 grid) {
     const bool hb = c->d_hit != nullptr, batch = c->layers > 1;
     const CamDev *cams = c->d_cams;
-#define UVT_LAUNCH(HB, BATCH) primary_kernel<World, COUNT, HB, BATCH><<<grid, kThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters)
+#define UVT_LAUNCH(HB, BATCH) primary_kernel<World, COUNT, HB, BATCH><<<grid, kTileThreads, 0, c->stream>>>(wa, cams, c->cam0, v, g, c->d_counters)
     if (hb) { if (batch) UVT_LAUNCH(true, true); else UVT_LAUNCH(true, false); }
     else { if (batch) UVT_LAUNCH(false, true); else UVT_LAUNCH(false, false); }
 #undef UVT_LAUNCH
@@ -514,9 +514,9 @@ int launch_secondary(uvt_ctx *c) {
     const GBufDev g = make_gbuf(c);
     const dim3 grid = trace_grid(c);
     if (use_pool(c)) secondary_pool_kernel<COUNT><<<pool_grid(c), kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
-    else if (COUNT != 1 && use_dense(c)) secondary_kernel<WorldDense, COUNT><<<grid, kThreads, 0, c->stream>>>(world_dense(c), v, g, c->d_counters);
-    else if (use_compact(c)) secondary_kernel<WorldCompact, COUNT><<<grid, kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
-    else secondary_kernel<WorldRef, COUNT><<<grid, kThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
+    else if (COUNT != 1 && use_dense(c)) secondary_kernel<WorldDense, COUNT><<<grid, kTileThreads, 0, c->stream>>>(world_dense(c), v, g, c->d_counters);
+    else if (use_compact(c)) secondary_kernel<WorldCompact, COUNT><<<grid, kTileThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
+    else secondary_kernel<WorldRef, COUNT><<<grid, kTileThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
     int rc = check_launch(c, "secondary_kernel");
     if (rc != UVT_OK) return rc;
     return launch_entity_shadow(c, v, g, storage_rows(c->H, c->band_rows, c->n_parts, c->part), c->layers);
@@ -1424,14 +1424,14 @@ int uvt_dispatch_frame(uvt_ctx *c) {
     const FrameTarget ft = make_target(c);
     ensure_sun(c);
     if (use_dense(c)) {
-        if (batch) frame_kernel<WorldDense, true, true><<<grid, kThreads, 0, c->stream>>>(world_dense(c), cams, c->cam0, v, ss, g, ft);
-        else frame_kernel<WorldDense, true, false><<<grid, kThreads, 0, c->stream>>>(world_dense(c), cams, c->cam0, v, ss, g, ft);
+        if (batch) frame_kernel<WorldDense, true, true><<<grid, kTileThreads, 0, c->stream>>>(world_dense(c), cams, c->cam0, v, ss, g, ft);
+        else frame_kernel<WorldDense, true, false><<<grid, kTileThreads, 0, c->stream>>>(world_dense(c), cams, c->cam0, v, ss, g, ft);
     } else if (use_compact(c)) {
-        if (batch) frame_kernel<WorldCompact, true, true><<<grid, kThreads, 0, c->stream>>>(world_compact(c), cams, c->cam0, v, ss, g, ft);
-        else frame_kernel<WorldCompact, true, false><<<grid, kThreads, 0, c->stream>>>(world_compact(c), cams, c->cam0, v, ss, g, ft);
+        if (batch) frame_kernel<WorldCompact, true, true><<<grid, kTileThreads, 0, c->stream>>>(world_compact(c), cams, c->cam0, v, ss, g, ft);
+        else frame_kernel<WorldCompact, true, false><<<grid, kTileThreads, 0, c->stream>>>(world_compact(c), cams, c->cam0, v, ss, g, ft);
     } else {
-        if (batch) frame_kernel<WorldRef, true, true><<<grid, kThreads, 0, c->stream>>>(world_ref(c), cams, c->cam0, v, ss, g, ft);
-        else frame_kernel<WorldRef, true, false><<<grid, kThreads, 0, c->stream>>>(world_ref(c), cams, c->cam0, v, ss, g, ft);
+        if (batch) frame_kernel<WorldRef, true, true><<<grid, kTileThreads, 0, c->stream>>>(world_ref(c), cams, c->cam0, v, ss, g, ft);
+        else frame_kernel<WorldRef, true, false><<<grid, kTileThreads, 0, c->stream>>>(world_ref(c), cams, c->cam0, v, ss, g, ft);
     }
     return check_launch(c, "frame_kernel");
 }
@@ -1899,9 +1899,9 @@ int launch_rows(uvt_ctx *c, uint32_t row0, uint32_t nrows) {
     if (rc == UVT_OK) rc = launch_entity_primary(c, v, g, nrows, 1);
     if (rc != UVT_OK) return rc;
     v.max_steps = c->params.shadow_max_steps;
-    if (use_dense(c)) secondary_kernel<WorldDense, 0><<<grid, kThreads, 0, c->stream>>>(world_dense(c), v, g, c->d_counters);
-    else if (use_compact(c)) secondary_kernel<WorldCompact, 0><<<grid, kThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
-    else secondary_kernel<WorldRef, 0><<<grid, kThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
+    if (use_dense(c)) secondary_kernel<WorldDense, 0><<<grid, kTileThreads, 0, c->stream>>>(world_dense(c), v, g, c->d_counters);
+    else if (use_compact(c)) secondary_kernel<WorldCompact, 0><<<grid, kTileThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
+    else secondary_kernel<WorldRef, 0><<<grid, kTileThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
     rc = check_launch(c, "secondary_kernel");
     if (rc == UVT_OK) rc = launch_entity_shadow(c, v, g, nrows, 1);
     if (rc != UVT_OK) return rc;
