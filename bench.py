@@ -612,7 +612,7 @@ def measure(uvt, torch, D, args, workload, steps, warmup, models, world_cache, w
                                      "rank0_rx_over_expected": round(d[0][0] / steps / expect, 4) if expect else None,
                                      "note": "expected = the (N-1)/N of the RGBA8 frame that the other ranks' bands hold (payload); the counters also see whatever else crosses NVLink in the timed region (the per-step barrier-free loop has no other traffic; NCCL adds its protocol)"}
                 else:
-                    rec["nvlink"] = {"unavailable": nvl.err}
+                    rec["nvlink"] = {"unavailable": nvl.err, "evidence": "profiles/r02_nvlink_p2p.md: ncu nvltx__bytes_data_user of every sender's shade_kernel == its band bytes"}
             if e2e_ok is not None:
                 rec["e2e"]["host_frame_equals_device_frame"] = e2e_ok
         if want_cpu_baseline:
