@@ -174,3 +174,33 @@ def test_committed_golden_is_the_reference_shader_output(uvt, oracle, glslref, w
     for k in ("albedo", "normal", "illumination", "frame"):
         assert np.array_equal(g[k], gold[k]) and np.array_equal(r[k], gold[k]), k
     assert np.array_equal(g["position"].view(np.uint32), gold["position"].view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_worlds_and_cameras(uvt, oracle, glslref, models, atlas, seed):
+    """Seeded random 64^3 worlds (random blocks of every loaded model, solid and not, unloaded model ids, blocks on the map
+    faces), random cameras inside / outside the map, random fov and frame size: oracle.c == the reference's shader text,
+    every image, bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    dim = 64
+    bm = uvt.voxel.VoxelBrickmap.init(dim)
+    n_models = len(models)
+    for _ in range(int(rng.integers(50, 1500))):
+        x, y, z = (int(v) for v in rng.integers(0, dim, 3))
+        if rng.random() < 0.1:
+            x = int(rng.choice([0, dim - 1]))
+        ty = int(rng.integers(0, n_models + (3 if seed % 4 == 0 else 0)))   # ids past the atlas: unloaded models read as empty
+        bm.set(x, y, z, ty | (int(rng.integers(0, 2)) << 28))
+    if seed % 3 == 0:   # a floor, so that shadows and sub-voxel grazing happen
+        for x in range(dim):
+            for z in range(dim):
+                bm.set(x, 3, z, int(rng.integers(0, 6)) | (1 << 28))
+    world = oracle.World(dim, bm.chunks().copy(), bm.bricks().copy(), atlas)
+    for _ in range(3):
+        inside = rng.random() < 0.7
+        pos = rng.uniform(2, dim - 2, 3) if inside else rng.uniform(-30, dim + 30, 3)
+        cam = oracle.make_camera(tuple(float(v) for v in pos), pitch_yaw_matrix(uvt, float(rng.uniform(-1.4, 1.4)), float(rng.uniform(0, 2 * np.pi))),
+                                 float(rng.uniform(0.5, 2.4)))
+        W, H = int(rng.integers(8, 120)), int(rng.integers(8, 90))
+        r = oracle.render(world, cam, W, H, oracle.params(dim))
+        assert_same_frame(r, glslref.render(world, cam, W, H))
