@@ -430,6 +430,40 @@ __global__ void __launch_bounds__(256) shade_kernel(ViewDev v, GBufDev gb, Frame
     else ft.ptr[i] = out;
 }
 
+// ---- secondary pass + blit of the same pixel in one launch (uvt_dispatch_frame) ---------------------
+// The illumination texel is stored as always (it is an output image of the reference), but the blit takes it from the register
+// instead of reading it back, and one launch with its tail is gone.  Same shadow_pixel, same shade_pixel: identical pixels.
+template <class World>
+__global__ void __launch_bounds__(kTileThreads, UVT_MIN_BLOCKS) secondary_shade_kernel(WorldArgs<World> wa, ViewDev v, GBufDev gb, FrameTarget ft) {
+    __shared__ uint32_t s_masks[(UVT_SMEM_MASKS && kIsCompact<World>) ? kSmemMaskMats * 16 : 1];
+    World w = wa.w;
+    if constexpr (kIsCompact<World>) {
+        stage_masks(s_masks, wa.masks, wa.n_mats);
+        w.smem_masks = s_masks;
+    }
+    uint32_t x, ly, y;
+    tile_pixel(x, ly);
+    ly += v.row0;
+    const bool valid = v.global_row(ly, y) && x < v.W;
+    TripCounts tc = {0, 0, 0};
+    uint32_t hit = 0;
+    const size_t i = (size_t)blockIdx.z * gb.layer_pixels + (size_t)ly * v.W + x;
+    float4 pos = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+    uint32_t nrm = 0;
+    if (valid) {
+        pos = gb.position[i];
+        nrm = gb.normal[i];
+    }
+    const bool shoot = valid && !(pos.x < 0.0f || pos.y < 0.0f || pos.z < 0.0f);  // secondary.comp.glsl:26-29
+    const uint32_t il = shadow_pixel<World, 0>(w, shoot, v, pos.x, pos.y, pos.z, nrm, tc, hit);  // all 32 lanes
+    if (!valid) return;
+    const uint32_t illum = shoot ? il : 0u;
+    gb.illum[i] = illum;
+    const uint32_t out = shade_pixel(v, x, y, gb.albedo[i], illum);
+    if (ft.global_rows) ft.ptr[(size_t)y * v.W + x] = out;
+    else ft.ptr[i] = out;
+}
+
 // ---- fused frame: primary + secondary + shade in one launch -------------------------------
 // Results are identical to the three separate passes: the shadow ray starts from the same
 // quantised position/normal the G-buffer would hold.

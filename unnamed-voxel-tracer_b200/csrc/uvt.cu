@@ -522,6 +522,18 @@ int launch_secondary(uvt_ctx *c) {
     return launch_entity_shadow(c, v, g, storage_rows(c->H, c->band_rows, c->n_parts, c->part), c->layers);
 }
 
+// secondary pass + blit in one launch over `nrows` local rows from v.row0 (the frame paths, when no entity pass sits between them)
+bool fuse_shade(const uvt_ctx *c) { return !use_pool(c) && !(ent_custom(c) && (c->params.flags & UVT_FLAG_ENTITIES)); }
+
+int launch_secondary_shade(uvt_ctx *c, const ViewDev &v, const GBufDev &g, dim3 grid) {
+    ensure_sun(c);
+    const FrameTarget ft = make_target(c);
+    if (use_dense(c)) secondary_shade_kernel<WorldDense><<<grid, kTileThreads, 0, c->stream>>>(world_dense(c), v, g, ft);
+    else if (use_compact(c)) secondary_shade_kernel<WorldCompact><<<grid, kTileThreads, 0, c->stream>>>(world_compact(c), v, g, ft);
+    else secondary_shade_kernel<WorldRef><<<grid, kTileThreads, 0, c->stream>>>(world_ref(c), v, g, ft);
+    return check_launch(c, "secondary_shade_kernel");
+}
+
 // Build the B200 layout from the committed reference layout (all on the device):
 // chunk distance field -> virtual bricks -> chunks2, 8-bit material bricks, block clearances.
 // scratch layout of uvt_world_commit_region (32-bit words)
@@ -1409,6 +1421,14 @@ int uvt_dispatch_frame(uvt_ctx *c) {
             PassTimer tp(c, 0);
             rc = launch_primary<0>(c);
         }
+        if (rc == UVT_OK && fuse_shade(c)) {  // shadow pass and blit in one launch; the blit's own timer brackets nothing
+            {
+                PassTimer ts(c, 1);
+                rc = launch_secondary_shade(c, make_view(c, c->params.shadow_max_steps), g, grid);
+            }
+            PassTimer tb(c, 2);
+            return rc;
+        }
         if (rc == UVT_OK) {
             PassTimer ts(c, 1);
             rc = launch_secondary<0>(c);
@@ -1899,6 +1919,7 @@ int launch_rows(uvt_ctx *c, uint32_t row0, uint32_t nrows) {
     if (rc == UVT_OK) rc = launch_entity_primary(c, v, g, nrows, 1);
     if (rc != UVT_OK) return rc;
     v.max_steps = c->params.shadow_max_steps;
+    if (fuse_shade(c)) return launch_secondary_shade(c, v, g, grid);
     if (use_dense(c)) secondary_kernel<WorldDense, 0><<<grid, kTileThreads, 0, c->stream>>>(world_dense(c), v, g, c->d_counters);
     else if (use_compact(c)) secondary_kernel<WorldCompact, 0><<<grid, kTileThreads, 0, c->stream>>>(world_compact(c), v, g, c->d_counters);
     else secondary_kernel<WorldRef, 0><<<grid, kTileThreads, 0, c->stream>>>(world_ref(c), v, g, c->d_counters);
