@@ -1486,18 +1486,24 @@ int uvt_set_entities(uvt_ctx *c, const float *positions_xyz, uint32_t n) {
 int uvt_entity_model_upload(uvt_ctx *c, uint32_t size, const uint32_t *rgba, uint32_t max_steps) {
     if (!c) return UVT_ERR_INVALID;
     UVT_ENTER(c);
+    const uint32_t steps = max_steps ? max_steps : 64u;
+    UVT_REQUIRE(c, steps <= 65535u, "entity step cap above 65535");
+    UVT_REQUIRE(c, !rgba || size == 8 || size == 16 || size == 32, "entity model edge must be 8, 16 or 32 voxels");
+    uint32_t *d_new = nullptr;
+    if (rgba) {  // build the new model first: a failure leaves the current one in place
+        const size_t bytes = (size_t)size * size * size * 4;
+        UVT_CUDA(c, cudaMalloc(&d_new, bytes));
+        cudaError_t e = cudaMemcpy(d_new, rgba, bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d_new);
+            return set_error(c, UVT_ERR_CUDA, "entity model upload: %s", cudaGetErrorString(e));
+        }
+    }
     UVT_CUDA(c, cudaStreamSynchronize(c->stream));  // a frame in flight may still read the old model
     cudaFree(c->d_ent_model);
-    c->d_ent_model = nullptr;
-    c->ent_size = 8;
-    c->ent_steps = max_steps ? max_steps : 64u;
-    UVT_REQUIRE(c, c->ent_steps <= 65535u, "entity step cap above 65535");
-    if (!rgba) return UVT_OK;  // back to the atlas texels [0,8)^3
-    UVT_REQUIRE(c, size == 8 || size == 16 || size == 32, "entity model edge must be 8, 16 or 32 voxels");
-    const size_t bytes = (size_t)size * size * size * 4;
-    UVT_CUDA(c, cudaMalloc(&c->d_ent_model, bytes));
-    UVT_CUDA(c, cudaMemcpy(c->d_ent_model, rgba, bytes, cudaMemcpyHostToDevice));
-    c->ent_size = size;
+    c->d_ent_model = d_new;          // nullptr: back to the atlas texels [0,8)^3
+    c->ent_size = rgba ? size : 8u;
+    c->ent_steps = steps;
     return UVT_OK;
 }
 
