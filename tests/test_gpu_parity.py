@@ -402,6 +402,16 @@ def test_errors_are_reported_not_fatal(uvt, oracle):
             ctx.readback("hit")              # hit buffer not enabled
         with pytest.raises(uvt.UvtError):
             ctx.set_partition(5, 2, 0)       # band not a multiple of 8
+        with pytest.raises(uvt.UvtError):
+            ctx.set_entities(np.zeros((33, 3), np.float32))          # more than 32 entities
+        with pytest.raises(uvt.UvtError):
+            ctx.entity_model_upload(np.zeros(12 ** 3, np.uint32), 12)  # edge not 8 / 16 / 32
+        with pytest.raises(uvt.UvtError):
+            ctx.set_frame_chunks(0)
+        with pytest.raises(uvt.UvtError):
+            ctx.check(ctx.L.uvt_set_entity_mode(ctx.handle, 7))
+        ctx.set_entity_mode("models")        # turns the hit buffer on: the G-buffer is re-created with one
+        assert ctx.readback("hit").shape == (32, 32)
 
 
 def test_world_edit_then_recommit(uvt, oracle, scene_factory):
