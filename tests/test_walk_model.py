@@ -125,3 +125,40 @@ def test_free_trips_granted_by_the_walk_are_free(uvt, oracle, atlas, seed):
 
 def world_block_nonempty(bm, o):
     return bm.get(int(o[0]), int(o[1]), int(o[2])) != 0
+
+
+def test_block_clearance_bound(uvt, oracle, atlas):
+    """The free-trip bound of the dense grid: with D the Chebyshev distance (blocks) from the looked-up empty block
+    to the nearest non-empty block or map face, the D - 2 trips that follow look up empty in-map blocks, whatever the direction."""
+    dim = 64
+    rng = np.random.default_rng(77)
+    bm = uvt.voxel.VoxelBrickmap.init(dim)
+    occ = np.zeros((dim, dim, dim), bool)   # [x, y, z]
+    for _ in range(260):
+        x, y, z = (int(v) for v in rng.integers(0, dim, 3))
+        bm.set(x, y, z, int(rng.integers(0, 29)) | (1 << 28))
+        occ[x, y, z] = True
+    world = oracle.World(dim, bm.chunks().copy(), bm.bricks().copy(), atlas)
+    pts = np.argwhere(occ)
+    checked = 0
+    for i in range(6000):
+        b = rng.integers(0, dim, 3)
+        if occ[tuple(b)]:
+            continue
+        D = int(np.abs(pts - b).max(axis=1).min())
+        D = min(D, int(min(b.min() + 1, (dim - b).min())), 16)
+        if D < 3:
+            continue
+        f = rng.choice([0.0, 1e-6, 0.5, 0.999999], 3) if i % 2 else rng.random(3)
+        o = (b + f).astype(np.float32)
+        if (o.astype(np.int64) != b).any():
+            continue
+        d = rng.normal(size=3)
+        d = (d / np.linalg.norm(d)).astype(np.float32)
+        if i % 5 == 0:
+            d[rng.integers(3)] = 0.0
+        n = D - 2
+        h = oracle.trace_map(world, o, d, n + 1)
+        assert h["t_block"] == 0 and h["data"] == 0 and h["exit_kind"] == 1, (b, D, o, d, h)
+        checked += 1
+    assert checked > 2500
