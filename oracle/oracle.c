@@ -8,7 +8,7 @@
  * The reference is GLSL 4.50 compute + Zig/OpenGL host code and cannot be run as a program in
  * this image (no Zig, no GL, no Mesa: SURVEY.md §8c), and it holds no golden vectors or
  * known-answer tests for this path.  What pins this restatement:
- * (1) oracle/_ref/libglslref.so — the reference's OWN shader text (assets/shaders/*.glsl, read
+ * (1) oracle/_ref/libglslref.so — the reference's OWN shader text (assets/shaders/ *.glsl, read
  *     where it lies, translated by syntactic rewrites only and compiled for the CPU against a
  *     GLSL-in-C++ shim: oracle/glsl_ref/).  tests/test_glsl_reference.py holds this file to it
  *     bit for bit: every G-buffer image, the illumination image and the final frame, traceMap,
