@@ -199,6 +199,8 @@ int  uvt_local_rows(uvt_ctx *ctx, uint32_t *rows);
 int  uvt_dispatch_primary(uvt_ctx *ctx);    /* primary.comp.glsl main   */
 int  uvt_dispatch_secondary(uvt_ctx *ctx);  /* secondary.comp.glsl main */
 int  uvt_shade(uvt_ctx *ctx);               /* blit.fragment.glsl main → RGBA8 frame */
+/* the two calls above in ONE launch (what uvt_dispatch_frame runs after the primary pass): same illumination image, same frame */
+int  uvt_dispatch_secondary_shade(uvt_ctx *ctx);
 /* primary+secondary+shade in one launch; results identical to the three calls above */
 int  uvt_dispatch_frame(uvt_ctx *ctx);
 /* ---- entities: traceEntities (assets/shaders/map.glsl:172-248), SURVEY 8 row f3 ----------------------

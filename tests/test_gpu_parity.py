@@ -114,6 +114,10 @@ def test_dispatch_frame_equals_three_passes(uvt, oracle, w1):
     cam = camera_k1(uvt, oracle)
     a = gpu_render(ctx, cam, three_pass=True)
     b = gpu_render(ctx, cam, three_pass=False)
+    ctx.dispatch_primary()
+    ctx.dispatch_secondary_shade()     # the shadow pass and the blit in one launch
+    for k in ("illumination", "frame"):
+        assert np.array_equal(a[k], ctx.readback(k)), k
     for k in ("albedo", "normal", "illumination", "frame"):
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(a["position"].view(np.uint32), b["position"].view(np.uint32))

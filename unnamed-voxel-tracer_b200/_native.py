@@ -81,6 +81,7 @@ SIGNATURES = {
     "uvt_dispatch_primary": (c_int, [c_p]),
     "uvt_dispatch_secondary": (c_int, [c_p]),
     "uvt_shade": (c_int, [c_p]),
+    "uvt_dispatch_secondary_shade": (c_int, [c_p]),
     "uvt_dispatch_frame": (c_int, [c_p]),
     "uvt_set_entity_mode": (c_int, [c_p, c_u32]),
     "uvt_set_entities": (c_int, [c_p, c_p, c_u32]),

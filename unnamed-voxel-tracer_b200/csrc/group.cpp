@@ -219,10 +219,9 @@ int uvt_group_resize(uvt_group *g, uint32_t width, uint32_t height) {
 
 int uvt_group_dispatch_frame(uvt_group *g) {
     if (!g) return UVT_ERR_INVALID;
-    // pass by pass rather than member by member: every device starts after n launches instead of 3n (all asynchronous)
+    // pass by pass rather than member by member: every device starts after n launches instead of 2n (all asynchronous)
     UVT_EACH(g, uvt_dispatch_primary(m));
-    UVT_EACH(g, uvt_dispatch_secondary(m));
-    UVT_EACH(g, uvt_shade(m));
+    UVT_EACH(g, uvt_dispatch_secondary_shade(m));  // shadow pass + blit (with the peer stores of the bands) in one launch per member
     return UVT_OK;
 }
 

@@ -1365,6 +1365,19 @@ int uvt_dispatch_secondary(uvt_ctx *c) {
     return launch_secondary<0>(c);
 }
 
+int uvt_dispatch_secondary_shade(uvt_ctx *c) {
+    if (!c) return UVT_ERR_INVALID;
+    UVT_ENTER(c);
+    int rc = pre_dispatch(c);
+    if (rc != UVT_OK) return rc;
+    if (!fuse_shade(c)) {  // pooled scheduler, or an entity pass sits between the two: the separate kernels
+        rc = uvt_dispatch_secondary(c);
+        return rc == UVT_OK ? uvt_shade(c) : rc;
+    }
+    PassTimer t(c, 1);
+    return launch_secondary_shade(c, make_view(c, c->params.shadow_max_steps), make_gbuf(c), trace_grid(c));
+}
+
 int uvt_shade(uvt_ctx *c) {
     if (!c) return UVT_ERR_INVALID;
     UVT_ENTER(c);

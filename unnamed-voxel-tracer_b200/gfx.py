@@ -139,6 +139,10 @@ class Context:
     def shade(self):
         self.check(self.L.uvt_shade(self.handle))
 
+    def dispatch_secondary_shade(self):
+        """dispatch_secondary() + shade() in one launch."""
+        self.check(self.L.uvt_dispatch_secondary_shade(self.handle))
+
     def dispatch_frame(self):
         self.check(self.L.uvt_dispatch_frame(self.handle))
 
